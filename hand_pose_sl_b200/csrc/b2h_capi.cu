@@ -1,0 +1,243 @@
+// extern "C" surface of libb2h.so (see include/b2h.h).  Argument checking, error reporting and
+// dispatch between the fp32 (FFMA) and bf16 (tcgen05) kernels.  No CPU fallback exists anywhere.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cmath>
+
+#include "b2h_common.cuh"
+
+namespace b2h {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return B2H_ECUDA;
+  }
+  return B2H_OK;
+}
+void count_launch(int n) { g_launches.fetch_add(n); }
+
+static bool geo_ok(int n_in, int C, int pos_emb, const char* who) {
+  if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || (pos_emb != 0 && pos_emb != 1)) {
+    set_error("%s: unsupported geometry n_in=%d C=%d pos_emb=%d", who, n_in, C, pos_emb);
+    return false;
+  }
+  return true;
+}
+
+static int train_nparts(const Geo& g, int B, int T, int precision) {
+  (void)precision;
+  return fp32_train_grid(g, B, T);
+}
+
+}  // namespace b2h
+
+using namespace b2h;
+
+extern "C" const char* b2h_last_error(void) { return g_err; }
+extern "C" int b2h_version(void) { return 100; }
+extern "C" int64_t b2h_launch_count(void) { return g_launches.load(); }
+
+extern "C" int b2h_device_ok(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int64_t b2h_param_count(int n_in, int C, int pos_emb) {
+  if (!geo_ok(n_in, C, pos_emb, "b2h_param_count")) return B2H_ESHAPE;
+  return make_geo(n_in, C, pos_emb).P;
+}
+extern "C" int64_t b2h_param_offset(int n_in, int C, int pos_emb, int layer, int is_bias) {
+  if (!geo_ok(n_in, C, pos_emb, "b2h_param_offset")) return B2H_ESHAPE;
+  if (layer < 1 || layer > 4) { set_error("b2h_param_offset: layer %d", layer); return B2H_EINVAL; }
+  Geo g = make_geo(n_in, C, pos_emb);
+  return is_bias ? g.b_off[layer - 1] : g.w_off[layer - 1];
+}
+extern "C" int64_t b2h_packed_bytes(int n_in, int C, int pos_emb) {
+  if (!geo_ok(n_in, C, pos_emb, "b2h_packed_bytes")) return B2H_ESHAPE;
+  return make_geo(n_in, C, pos_emb).packed_bytes;
+}
+extern "C" int b2h_supported(int T, int n_in, int C, int pos_emb, int precision) {
+  if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1) return 0;
+  Geo g = make_geo(n_in, C, pos_emb);
+  if (precision == B2H_FP32) return fp32_smem_bytes(g, T, true) <= (size_t)227 * 1024 ? 1 : 0;
+  if (precision == B2H_BF16) return (tc_fwd_supported(g, T) && fp32_smem_bytes(g, T, true) <= (size_t)227 * 1024) ? 1 : 0;
+  return 0;
+}
+extern "C" int64_t b2h_workspace_bytes(int B, int T, int n_in, int C, int pos_emb, int precision) {
+  if (!geo_ok(n_in, C, pos_emb, "b2h_workspace_bytes")) return B2H_ESHAPE;
+  if (B < 1 || T < 1) return 256;
+  Geo g = make_geo(n_in, C, pos_emb);
+  const int np = train_nparts(g, B, T, precision);
+  return ((int64_t)np * g.P + np) * 4 + 256;
+}
+
+extern "C" int b2h_pack_weights(const float* params, void* packed, int n_in, int C, int pos_emb, void* stream) {
+  if (!params || !packed) { set_error("b2h_pack_weights: null pointer"); return B2H_EINVAL; }
+  if (!geo_ok(n_in, C, pos_emb, "b2h_pack_weights")) return B2H_ESHAPE;
+  return launch_pack(params, packed, make_geo(n_in, C, pos_emb), (cudaStream_t)stream);
+}
+
+extern "C" int b2h_conv_forward(const void* x, int x_dtype, const float* params, const void* packed, const int32_t* lengths,
+                                float* y, int B, int T, int n_in, int C, int pos_emb, int precision, int apply_mask,
+                                float out_scale, void* stream) {
+  if (!x || !params || !packed || !y) { set_error("b2h_conv_forward: null pointer"); return B2H_EINVAL; }
+  if (x_dtype != B2H_DT_F32 && x_dtype != B2H_DT_BF16) { set_error("b2h_conv_forward: bad x_dtype %d", x_dtype); return B2H_EINVAL; }
+  if (!geo_ok(n_in, C, pos_emb, "b2h_conv_forward")) return B2H_ESHAPE;
+  if (B < 0 || T < 1) { set_error("b2h_conv_forward: bad B=%d T=%d", B, T); return B2H_ESHAPE; }
+  if (apply_mask && !lengths) { set_error("b2h_conv_forward: apply_mask needs lengths"); return B2H_EINVAL; }
+  if (B == 0) return B2H_OK;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(packed) & 15)) {
+    set_error("b2h_conv_forward: x, y and packed must be 16-byte aligned");
+    return B2H_EALIGN;
+  }
+  Geo g = make_geo(n_in, C, pos_emb);
+  if (precision == B2H_FP32) {
+    Fp32Args a{};
+    a.x = x; a.x_dtype = x_dtype; a.lengths = lengths; a.params = params; a.packed = reinterpret_cast<const char*>(packed);
+    a.y = y; a.B = B; a.T = T; a.apply_mask = apply_mask; a.mode = 0; a.out_scale = out_scale; a.geo = g;
+    return launch_fp32(a, false, (cudaStream_t)stream, 0);
+  } else if (precision == B2H_BF16) {
+    TcFwdArgs a{};
+    a.x = x; a.x_dtype = x_dtype; a.params = params; a.packed = reinterpret_cast<const char*>(packed); a.lengths = lengths;
+    a.y = y; a.B = B; a.T = T; a.apply_mask = apply_mask; a.out_scale = out_scale; a.geo = g;
+    return launch_tc_fwd(a, (cudaStream_t)stream);
+  }
+  set_error("b2h_conv_forward: bad precision %d", precision);
+  return B2H_EINVAL;
+}
+
+static int train_common(const void* x, int x_dtype, const float* target, const float* conf, const float* d_y,
+                        const int32_t* lengths, const float* params, const void* packed, float* pred_out, int B, int T,
+                        int n_in, int C, int pos_emb, int loss_kind, int precision, int mode, void* workspace,
+                        int64_t workspace_bytes, cudaStream_t stream, Geo& g, int& nparts, float*& partials,
+                        float*& loss_partials, const char* who) {
+  if (!x || !params || !packed || !workspace) { set_error("%s: null pointer", who); return B2H_EINVAL; }
+  if (x_dtype != B2H_DT_F32 && x_dtype != B2H_DT_BF16) { set_error("%s: bad x_dtype %d", who, x_dtype); return B2H_EINVAL; }
+  if (!geo_ok(n_in, C, pos_emb, who)) return B2H_ESHAPE;
+  if (B < 1 || T < 1) { set_error("%s: bad B=%d T=%d", who, B, T); return B2H_ESHAPE; }
+  if (precision != B2H_FP32 && precision != B2H_BF16) { set_error("%s: bad precision %d", who, precision); return B2H_EINVAL; }
+  if (mode == 1) {
+    if (!target || !lengths) { set_error("%s: null target/lengths", who); return B2H_EINVAL; }
+    if (loss_kind != B2H_LOSS_L1 && loss_kind != B2H_LOSS_CONFL1) { set_error("%s: bad loss_kind %d", who, loss_kind); return B2H_EINVAL; }
+    if (loss_kind == B2H_LOSS_CONFL1 && !conf) { set_error("%s: confL1 needs scores", who); return B2H_EINVAL; }
+  } else if (!d_y) { set_error("%s: null d_y", who); return B2H_EINVAL; }
+  g = make_geo(n_in, C, pos_emb);
+  nparts = train_nparts(g, B, T, precision);
+  const int64_t need = ((int64_t)nparts * g.P + nparts) * 4;
+  if (workspace_bytes < need) { set_error("%s: workspace %lld B < %lld B", who, (long long)workspace_bytes, (long long)need); return B2H_EWORKSPACE; }
+  partials = reinterpret_cast<float*>(workspace);
+  loss_partials = partials + (size_t)nparts * g.P;
+  // Backward/training currently runs the FFMA kernel for both precisions (fp32 math, fp32 master
+  // weights); the bf16 tensor-core backward replaces it behind the same entry point.
+  Fp32Args a{};
+  a.x = x; a.x_dtype = x_dtype; a.target = target; a.conf = conf; a.d_y = d_y; a.lengths = lengths; a.params = params;
+  a.packed = reinterpret_cast<const char*>(packed); a.y = pred_out; a.partials = partials; a.loss_partials = loss_partials;
+  a.B = B; a.T = T; a.loss_kind = loss_kind; a.apply_mask = 1; a.mode = mode; a.out_scale = 1.0f; a.geo = g;
+  return launch_fp32(a, true, stream, nparts);
+}
+
+extern "C" int b2h_train_forward_backward(const void* x, int x_dtype, const float* target, const float* conf,
+                                          const int32_t* lengths, const float* params, const void* packed,
+                                          float* grads_out, float* loss_out, float* pred_out, int B, int T, int n_in,
+                                          int C, int pos_emb, int loss_kind, int precision, void* workspace,
+                                          int64_t workspace_bytes, void* stream) {
+  if (!grads_out || !loss_out) { set_error("b2h_train_forward_backward: null output"); return B2H_EINVAL; }
+  Geo g; int nparts; float *partials, *loss_partials;
+  int rc = train_common(x, x_dtype, target, conf, nullptr, lengths, params, packed, pred_out, B, T, n_in, C, pos_emb,
+                        loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
+                        loss_partials, "b2h_train_forward_backward");
+  if (rc) return rc;
+  return launch_reduce(partials, nparts, g.P, grads_out, loss_partials, loss_out, (cudaStream_t)stream);
+}
+
+extern "C" int b2h_conv_backward(const void* x, int x_dtype, const float* d_y, const float* params, const void* packed,
+                                 float* grads_out, int B, int T, int n_in, int C, int pos_emb, int precision,
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!grads_out) { set_error("b2h_conv_backward: null output"); return B2H_EINVAL; }
+  Geo g; int nparts; float *partials, *loss_partials;
+  int rc = train_common(x, x_dtype, nullptr, nullptr, d_y, nullptr, params, packed, nullptr, B, T, n_in, C, pos_emb, 0,
+                        precision, 2, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
+                        loss_partials, "b2h_conv_backward");
+  if (rc) return rc;
+  return launch_reduce(partials, nparts, g.P, grads_out, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int b2h_train_step(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,
+                              float* params, void* packed, float* exp_avg, float* exp_avg_sq, float* loss_out, int B,
+                              int T, int n_in, int C, int pos_emb, int loss_kind, int precision, double lr, double beta1,
+                              double beta2, double eps, int64_t step, void* workspace, int64_t workspace_bytes,
+                              void* stream) {
+  if (!exp_avg || !exp_avg_sq || !loss_out) { set_error("b2h_train_step: null pointer"); return B2H_EINVAL; }
+  if (step < 1) { set_error("b2h_train_step: step must be >= 1"); return B2H_EINVAL; }
+  Geo g; int nparts; float *partials, *loss_partials;
+  int rc = train_common(x, x_dtype, target, conf, nullptr, lengths, params, packed, nullptr, B, T, n_in, C, pos_emb,
+                        loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
+                        loss_partials, "b2h_train_step");
+  if (rc) return rc;
+  return launch_adam(params, partials, nparts, exp_avg, exp_avg_sq, g.P, lr, beta1, beta2, eps, step, 1.0f, packed, g,
+                     loss_partials, loss_out, (cudaStream_t)stream);
+}
+
+extern "C" int b2h_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                             double beta1, double beta2, double eps, int64_t step, float grad_scale, void* packed,
+                             int n_in, int C, int pos_emb, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq) { set_error("b2h_adam_step: null pointer"); return B2H_EINVAL; }
+  if (step < 1 || n < 0) { set_error("b2h_adam_step: bad step/n"); return B2H_EINVAL; }
+  Geo g{};
+  if (packed) {
+    if (!geo_ok(n_in, C, pos_emb, "b2h_adam_step")) return B2H_ESHAPE;
+    g = make_geo(n_in, C, pos_emb);
+    if (g.P != n) { set_error("b2h_adam_step: n=%lld does not match geometry (%d)", (long long)n, g.P); return B2H_ESHAPE; }
+  }
+  if (n == 0) return B2H_OK;
+  return launch_adam(params, grads, 1, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, packed, g, nullptr,
+                     nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int b2h_mask_output(float* y, const int32_t* lengths, int B, int T, int row_elems, void* stream) {
+  if (!y || !lengths) { set_error("b2h_mask_output: null pointer"); return B2H_EINVAL; }
+  if (B < 0 || T < 0 || row_elems < 1) { set_error("b2h_mask_output: bad shape"); return B2H_ESHAPE; }
+  return launch_mask_output(y, lengths, B, T, row_elems, (cudaStream_t)stream);
+}
+
+extern "C" int b2h_pose_l1(const float* pred, const float* target, const float* scores, const int32_t* lengths, int B, int T,
+                           int row_elems, int loss_kind, float* loss_out, float* d_pred, float* row_scratch, void* stream) {
+  if (!pred || !target || !lengths || !loss_out || !row_scratch) { set_error("b2h_pose_l1: null pointer"); return B2H_EINVAL; }
+  if (loss_kind != B2H_LOSS_L1 && loss_kind != B2H_LOSS_CONFL1) { set_error("b2h_pose_l1: bad loss_kind"); return B2H_EINVAL; }
+  if (loss_kind == B2H_LOSS_CONFL1 && (!scores || (row_elems & 1))) { set_error("b2h_pose_l1: confL1 needs scores and even row_elems"); return B2H_EINVAL; }
+  if (B < 1 || T < 1 || row_elems < 1) { set_error("b2h_pose_l1: bad shape"); return B2H_ESHAPE; }
+  return launch_pose_l1(pred, target, scores, lengths, B, T, row_elems, loss_kind, loss_out, d_pred, row_scratch, (cudaStream_t)stream);
+}
+
+extern "C" int b2h_tc_probe(const void* a_bf16, const void* b_bf16, float* out, int n, int ksteps, int shift, int variant,
+                            void* stream) {
+  if (!a_bf16 || !b_bf16 || !out) { set_error("b2h_tc_probe: null pointer"); return B2H_EINVAL; }
+  return launch_tc_probe(a_bf16, b_bf16, out, n, ksteps, shift, variant, (cudaStream_t)stream);
+}
+
+extern "C" int b2h_tc_status(void) { return tc_status_and_clear(); }
+
+int b2h::num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}

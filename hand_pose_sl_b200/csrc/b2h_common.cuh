@@ -1,0 +1,113 @@
+// Shared geometry / helpers for libb2h.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/b2h.h"
+
+#define B2H_KW 5          // kernel_size of every Conv1d (HandPoseModels.py:24-32)
+#define B2H_PADW 2        // padding=2
+#define B2H_COUT 42       // 2*21 output channels (HandPoseModels.py:32)
+#define B2H_MAX_C 256
+
+namespace b2h {
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Layout of the flat fp32 parameter buffer (state_dict order) and of the packed weight buffer.
+struct Geo {
+  int n_in, C, pos_emb;
+  int cin[4], cout[4];
+  int w_off[4], b_off[4];   // float offsets into the flat parameter buffer
+  int P;                    // total parameter count
+  // packed buffer (byte offsets, each 128-B aligned)
+  int64_t wf_off[4];        // fp32 forward taps   Wf[k][ci][co]            = W[co][ci][k]
+  int64_t wd_off[4];        // fp32 dgrad taps     Wd[k'][co][ci]           = W[co][ci][4-k']   (layers 2..4)
+  int64_t tf_off[4];        // bf16 UMMA B operand, forward  (blocks of [2][N][8])
+  int64_t td_off[4];        // bf16 UMMA B operand, dgrad    (layers 2..4)
+  int kp[4], np_[4];        // UMMA padded reduction (cin -> mult of 16) and N (cout -> mult of 16), forward
+  int64_t packed_bytes;
+};
+
+__host__ __device__ inline Geo make_geo(int n_in, int C, int pos_emb) {
+  Geo g;
+  g.n_in = n_in; g.C = C; g.pos_emb = pos_emb;
+  g.cin[0] = n_in + (pos_emb ? 1 : 0); g.cout[0] = C;
+  g.cin[1] = C; g.cout[1] = C;
+  g.cin[2] = C; g.cout[2] = C;
+  g.cin[3] = C; g.cout[3] = B2H_COUT;
+  int off = 0;
+  for (int l = 0; l < 4; ++l) {
+    g.w_off[l] = off; off += g.cout[l] * g.cin[l] * B2H_KW;
+    g.b_off[l] = off; off += g.cout[l];
+  }
+  g.P = off;
+  int64_t b = 0;
+  for (int l = 0; l < 4; ++l) { g.wf_off[l] = b; b += (int64_t)B2H_KW * g.cin[l] * g.cout[l] * 4; b = (b + 127) / 128 * 128; }
+  for (int l = 0; l < 4; ++l) { g.wd_off[l] = b; if (l > 0) { b += (int64_t)B2H_KW * g.cin[l] * g.cout[l] * 4; b = (b + 127) / 128 * 128; } }
+  for (int l = 0; l < 4; ++l) {
+    g.kp[l] = round_up(g.cin[l], 16); g.np_[l] = round_up(g.cout[l], 16);
+    g.tf_off[l] = b; b += (int64_t)B2H_KW * g.kp[l] * g.np_[l] * 2; b = (b + 127) / 128 * 128;
+  }
+  for (int l = 0; l < 4; ++l) {
+    g.td_off[l] = b;
+    if (l > 0) { b += (int64_t)B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2; b = (b + 127) / 128 * 128; }
+  }
+  g.packed_bytes = b;
+  return g;
+}
+
+// Byte offset inside one UMMA B-operand section of element (n, kk) of tap k.
+// Section = blocks q = k*(KP/16)+s of [2 k-chunks][N rows][8 bf16] (no-swizzle K-major canonical
+// layout: core matrix = 8 rows x 16 B, SBO = 128 B between 8-row groups, LBO = N*16 B between chunks).
+__host__ __device__ inline int64_t umma_b_offset(int k, int kk, int n, int KP, int N) {
+  int s = kk >> 4, chunk = (kk >> 3) & 1, within = kk & 7;
+  int64_t q = (int64_t)k * (KP >> 4) + s;
+  return q * ((int64_t)N * 32) + (int64_t)chunk * (N * 16) + (int64_t)n * 16 + within * 2;
+}
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+void count_launch(int n = 1);
+
+
+// ---- kernel argument blocks and launchers shared between translation units ----
+struct Fp32Args {
+  const void* x; int x_dtype;
+  const float* target; const float* conf; const float* d_y; const int32_t* lengths;
+  const float* params; const char* packed;
+  float* y;                 // forward output / masked prediction (nullable in train mode)
+  float* partials;          // [grid][P]
+  float* loss_partials;     // [grid]
+  int B, T, loss_kind, apply_mask, mode;   // mode 0 = forward, 1 = train (loss inside), 2 = backward of given d_y
+  float out_scale;
+  Geo geo;
+};
+int launch_fp32(Fp32Args& p, bool train, cudaStream_t stream, int grid_override);
+int fp32_train_grid(const Geo& g, int B, int T);
+size_t fp32_smem_bytes(const Geo& g, int T, bool train);
+
+struct TcFwdArgs {
+  const void* x; int x_dtype;
+  const float* params; const char* packed; const int32_t* lengths;
+  float* y;
+  int B, T, G, NT, RBUF, apply_mask;
+  float out_scale;
+  Geo geo;
+};
+int launch_tc_fwd(TcFwdArgs& p, cudaStream_t stream);
+bool tc_fwd_supported(const Geo& g, int T);
+int launch_tc_probe(const void* a, const void* b, float* out, int n, int ksteps, int shift, int variant, cudaStream_t stream);
+int tc_status_and_clear();
+
+int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t stream);
+int launch_reduce(const float* partials, int nparts, int P, float* grads, const float* loss_partials, float* loss_out, cudaStream_t stream);
+int launch_adam(float* params, const float* grads, int nparts, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                double eps, int64_t step, float grad_scale, void* packed, const Geo& g, const float* loss_partials, float* loss_out,
+                cudaStream_t stream);
+int launch_mask_output(float* y, const int32_t* lengths, int B, int T, int row, cudaStream_t stream);
+int launch_pose_l1(const float* pred, const float* target, const float* scores, const int32_t* lengths, int B, int T, int row,
+                   int loss_kind, float* loss_out, float* d_pred, float* row_scratch, cudaStream_t stream);
+int num_sms();
+
+}  // namespace b2h

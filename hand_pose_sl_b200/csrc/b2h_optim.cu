@@ -1,0 +1,202 @@
+// K3: gradient-partial reduction, fused Adam (+ re-pack of the updated weights into every operand
+// layout the conv kernels read), stand-alone weight packing, and the stand-alone criteria kernels of
+// the modular API (mask_output, maskedPoseL1 / poderatedPoseL1 value + gradient).
+//
+// Reference semantics (paths relative to the reference root):
+//   torch.optim.Adam(model.parameters(), lr)   body2hand/src/steps/traintest.py:48, :119-121
+//   mask_output                                body2hand/src/steps/utils.py:309-312
+//   maskedPoseL1 / poderatedPoseL1             body2hand/src/steps/utils.py:413-452
+#include "b2h_common.cuh"
+
+namespace b2h {
+
+// Scatter one fp32 parameter (flat index i) into the packed operand layouts.
+__device__ __forceinline__ void scatter_packed(const Geo& g, char* packed, int i, float v) {
+  int l = 0;
+#pragma unroll
+  for (int q = 1; q < 4; ++q)
+    if (i >= g.w_off[q]) l = q;
+  if (i >= g.b_off[l]) return;  // biases are read from the flat buffer directly
+  const int cin = g.cin[l], cout = g.cout[l];
+  const int rel = i - g.w_off[l];
+  const int co = rel / (cin * B2H_KW);
+  const int rem = rel - co * cin * B2H_KW;
+  const int ci = rem / B2H_KW, k = rem - ci * B2H_KW;
+  reinterpret_cast<float*>(packed + g.wf_off[l])[(k * cin + ci) * cout + co] = v;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(packed + g.tf_off[l] + umma_b_offset(k, ci, co, g.kp[l], g.np_[l])) = h;
+  if (l > 0) {
+    reinterpret_cast<float*>(packed + g.wd_off[l])[((B2H_KW - 1 - k) * cout + co) * cin + ci] = v;
+    *reinterpret_cast<__nv_bfloat16*>(packed + g.td_off[l] +
+                                      umma_b_offset(B2H_KW - 1 - k, co, ci, round_up(cout, 16), round_up(cin, 16))) = h;
+  }
+}
+
+__global__ void pack_kernel(const float* __restrict__ params, char* packed, Geo g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.P) scatter_packed(g, packed, i, params[i]);
+}
+
+// grads[i] = sum_c partials[c][i];  loss = sum_c loss_partials[c]   (fixed order -> deterministic)
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int nparts, int P, float* __restrict__ grads,
+                                       const float* __restrict__ loss_partials, float* __restrict__ loss_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P) {
+    float s = 0.f;
+    for (int c = 0; c < nparts; ++c) s += partials[(size_t)c * P + i];
+    grads[i] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32 && loss_out) {
+    float s = 0.f;
+    for (int c = threadIdx.x; c < nparts; c += 32) s += loss_partials[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *loss_out = s;
+  }
+}
+
+struct AdamArgs {
+  float* params; const float* grads; int nparts; int64_t n;
+  float* m; float* v;
+  float beta1, beta2, one_minus_b1, one_minus_b2, step_size, inv_bc2_sqrt, eps, grad_scale;
+  char* packed; Geo g;
+  const float* loss_partials; float* loss_out;
+};
+
+// torch.optim.Adam single-tensor update (defaults: amsgrad=False, weight_decay=0, maximize=False):
+//   m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2);
+//   denom = v.sqrt()/sqrt(1-b2^t) + eps;  p.addcdiv_(m, denom, value=-lr/(1-b1^t))
+__global__ void adam_kernel(AdamArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.n) {
+    float gr = 0.f;
+    for (int c = 0; c < a.nparts; ++c) gr += a.grads[(size_t)c * a.n + i];
+    gr *= a.grad_scale;
+    float m = a.m[i], v = a.v[i], p = a.params[i];
+    m = fmaf(gr - m, a.one_minus_b1, m);
+    v = fmaf(a.one_minus_b2 * gr, gr, v * a.beta2);
+    const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
+    p = p - a.step_size * (m / denom);
+    a.m[i] = m; a.v[i] = v; a.params[i] = p;
+    if (a.packed) scatter_packed(a.g, a.packed, (int)i, p);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32 && a.loss_out) {
+    float s = 0.f;
+    for (int c = threadIdx.x; c < a.nparts; c += 32) s += a.loss_partials[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *a.loss_out = s;
+  }
+}
+
+__global__ void mask_output_kernel(float* __restrict__ y, const int32_t* __restrict__ lengths, int B, int T, int row) {
+  const int64_t n = (int64_t)B * T * row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bt = i / row;
+    const int b = (int)(bt / T), t = (int)(bt - (int64_t)b * T);
+    if (t >= lengths[b]) y[i] = 0.0f;                     // output[i, len:, :] = 0   utils.py:311
+  }
+}
+
+// one CTA per sample: per-sample mean |d| over the first len frames (+ gradient)
+__global__ void __launch_bounds__(256) pose_l1_rows_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                                           const float* __restrict__ scores,
+                                                           const int32_t* __restrict__ lengths, int B, int T, int row,
+                                                           int loss_kind, float* __restrict__ d_pred,
+                                                           float* __restrict__ row_scratch) {
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  int len = lengths[b];
+  len = len < 0 ? 0 : (len > T ? T : len);
+  const float n_el = (float)len * (float)row;
+  const float scale = (loss_kind == B2H_LOSS_L1) ? (1.0f / (float)B) / n_el : 1.0f / n_el;
+  const size_t base = (size_t)b * T * row;
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < T * row; i += blockDim.x) {
+    const int t = i / row;
+    float gr = 0.f;
+    if (t < len) {
+      const float pr = pred[base + i], tv = target[base + i];
+      float d, s = 1.f;
+      if (loss_kind == B2H_LOSS_L1) {
+        d = pr - tv;
+      } else {
+        s = scores[((size_t)b * T + t) * (row >> 1) + ((i - t * row) >> 1)];
+        d = __fsub_rn(__fmul_rn(pr, s), __fmul_rn(tv, s));
+      }
+      sum += fabsf(d);
+      gr = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * s * scale;
+    }
+    if (d_pred) d_pred[base + i] = gr;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    row_scratch[b] = s / n_el;
+  }
+}
+
+__global__ void pose_l1_final_kernel(const float* __restrict__ row_scratch, int B, int loss_kind, float* __restrict__ loss_out) {
+  // sequential like the reference's python loop (loss += ...), then / B for maskedPoseL1
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += row_scratch[b];
+    *loss_out = (loss_kind == B2H_LOSS_L1) ? s / (float)B : s;
+  }
+}
+
+int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t stream) {
+  pack_kernel<<<(g.P + 255) / 256, 256, 0, stream>>>(params, reinterpret_cast<char*>(packed), g);
+  count_launch();
+  return check_launch("pack_kernel");
+}
+
+int launch_reduce(const float* partials, int nparts, int P, float* grads, const float* loss_partials, float* loss_out,
+                  cudaStream_t stream) {
+  reduce_partials_kernel<<<(P + 255) / 256, 256, 0, stream>>>(partials, nparts, P, grads, loss_partials, loss_out);
+  count_launch();
+  return check_launch("reduce_partials_kernel");
+}
+
+int launch_adam(float* params, const float* grads, int nparts, float* m, float* v, int64_t n, double lr, double beta1,
+                double beta2, double eps, int64_t step, float grad_scale, void* packed, const Geo& g,
+                const float* loss_partials, float* loss_out, cudaStream_t stream) {
+  AdamArgs a;
+  a.params = params; a.grads = grads; a.nparts = nparts; a.n = n; a.m = m; a.v = v;
+  a.beta1 = (float)beta1; a.beta2 = (float)beta2;
+  a.one_minus_b1 = (float)(1.0 - beta1); a.one_minus_b2 = (float)(1.0 - beta2);
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  a.step_size = (float)(lr / bc1);
+  a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  a.eps = (float)eps; a.grad_scale = grad_scale;
+  a.packed = reinterpret_cast<char*>(packed); a.g = g;
+  a.loss_partials = loss_partials; a.loss_out = loss_out;
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a);
+  count_launch();
+  return check_launch("adam_kernel");
+}
+
+int launch_mask_output(float* y, const int32_t* lengths, int B, int T, int row, cudaStream_t stream) {
+  int64_t n = (int64_t)B * T * row;
+  if (n == 0) return B2H_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  mask_output_kernel<<<(unsigned)blocks, 256, 0, stream>>>(y, lengths, B, T, row);
+  count_launch();
+  return check_launch("mask_output_kernel");
+}
+
+int launch_pose_l1(const float* pred, const float* target, const float* scores, const int32_t* lengths, int B, int T,
+                   int row, int loss_kind, float* loss_out, float* d_pred, float* row_scratch, cudaStream_t stream) {
+  if (B <= 0) return B2H_OK;
+  pose_l1_rows_kernel<<<B, 256, 0, stream>>>(pred, target, scores, lengths, B, T, row, loss_kind, d_pred, row_scratch);
+  pose_l1_final_kernel<<<1, 32, 0, stream>>>(row_scratch, B, loss_kind, loss_out);
+  count_launch(2);
+  return check_launch("pose_l1 kernels");
+}
+
+}  // namespace b2h

@@ -1,0 +1,274 @@
+// K0 -- keypoint preprocessing: 12-of-25 gather, xy/conf split, crop/pad windowing,
+// wrist/neck-relative differencing, /1280 normalisation.  HBM-bound, bit-exact.
+//
+// Reference semantics (paths relative to the reference root):
+//   load_keypoints / BODY_HEAD_KEYPOINTS     body2hand/src/dataloaders/text_pose_dataset.py:14-50
+//   select_jsons crop, pad, clip, n_frames   ...text_pose_dataset.py:52-68, 447, 511-529, 614-635
+//   WristDifference / ChestDifference        body2hand/src/steps/utils.py:194-210
+//   NormalizeFixedFactor                     body2hand/src/steps/utils.py:180-190
+//   BuildRightHandItem                       body2hand/src/steps/utils.py:261-277
+//   TextPoseH5Dataset.array2item             ...text_pose_dataset.py:587-612
+//
+// Design: one warp owns 4 consecutive window slots.  4 OpenPose frames are 1200 B (pose) +
+// 2 x 1008 B (hands): all three are 16-B multiples, so an aligned 4-frame group is moved
+// HBM -> shared memory with coalesced 128-bit loads (201 float4 per warp, all issued before the first
+// use), the wrist / neck references are shared through the staged tile, and the six output rows of the
+// 4 slots (162 float4) go back with coalesced 128-bit stores.  Padded / unaligned groups take a scalar
+// path inside the same kernel (warp-uniform branch).  IEEE sub.rn then div.rn: no reciprocal, no FMA.
+#include "b2h_common.cuh"
+
+namespace b2h {
+
+constexpr int kWarpsPerBlock = 8;
+
+template <int FMT> struct Fmt;
+// FMT 0: OpenPose [x,y,c] rows: pose25 (75) | hand_left (63) | hand_right (63)
+template <> struct Fmt<0> {
+  static constexpr int kBody = 12;
+  static constexpr int kSrc = 3;
+  static constexpr int kStage = 4 * (75 + 63 + 63);  // 804 floats per warp
+  __device__ static int src_len(int a) { return a == 0 ? 75 : 63; }
+  __device__ static int src_off(int a) { return a == 0 ? 0 : (a == 1 ? 300 : 552); }
+  __device__ static int body_idx(int j) { return j < 8 ? j : j + 7; }  // BODY_HEAD_KEYPOINTS
+  __device__ static float body(const float* st, int i, int j, int d) { return st[i * 75 + 3 * body_idx(j) + d]; }
+  __device__ static float lh(const float* st, int i, int j, int d) { return st[300 + i * 63 + 3 * j + d]; }
+  __device__ static float rh(const float* st, int i, int j, int d) { return st[552 + i * 63 + 3 * j + d]; }
+};
+// FMT 1: packed H5 rows (150) = [x0..x49 | y0..y49 | c0..c49]; body 0..7, left hand 8..28, right 29..49
+template <> struct Fmt<1> {
+  static constexpr int kBody = 8;
+  static constexpr int kSrc = 1;
+  static constexpr int kStage = 4 * 150;
+  __device__ static int src_len(int) { return 150; }
+  __device__ static int src_off(int) { return 0; }
+  __device__ static float body(const float* st, int i, int j, int d) { return st[i * 150 + d * 50 + j]; }
+  __device__ static float lh(const float* st, int i, int j, int d) { return st[i * 150 + d * 50 + 8 + j]; }
+  __device__ static float rh(const float* st, int i, int j, int d) { return st[i * 150 + d * 50 + 29 + j]; }
+};
+
+struct PreArgs {
+  const float* src[3];
+  int64_t n_frames;
+  const int64_t* win_start;
+  int n_win, T, pad_mode, dif, normalize, aligned;
+  float factor;
+  float* out[6];  // input_kp, input_conf, target_kp, target_conf, left_kp, left_conf
+  int64_t* n_frames_out;
+  __nv_bfloat16* input_bf16;
+};
+
+template <int FMT>
+__device__ __forceinline__ float out_elem(const float* st, int a, int i, int r, const PreArgs& p) {
+  using F = Fmt<FMT>;
+  float v;
+  switch (a) {
+    case 0: {  // input_kp = (body - neck) / factor          utils.py:209, :186, :265
+      int j = r >> 1, d = r & 1;
+      v = F::body(st, i, j, d);
+      if (p.dif) v = __fsub_rn(v, F::body(st, i, 1, d));
+      if (p.normalize) v = __fdiv_rn(v, p.factor);
+      return v;
+    }
+    case 1: return F::body(st, i, r, 2);  // input_conf     utils.py:268
+    case 2: {  // target_kp = (right_hand - raw right wrist) / factor   utils.py:200, :187, :266
+      int j = r >> 1, d = r & 1;
+      v = F::rh(st, i, j, d);
+      if (p.dif) v = __fsub_rn(v, F::body(st, i, 4, d));
+      if (p.normalize) v = __fdiv_rn(v, p.factor);
+      return v;
+    }
+    case 3: return F::rh(st, i, r, 2);    // target_conf    utils.py:269
+    case 4: {  // left hand is only scaled, never differenced    utils.py:188
+      int j = r >> 1, d = r & 1;
+      v = F::lh(st, i, j, d);
+      if (p.normalize) v = __fdiv_rn(v, p.factor);
+      return v;
+    }
+    default: return F::lh(st, i, r, 2);
+  }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) preprocess_kernel(PreArgs p) {
+  using F = Fmt<FMT>;
+  __shared__ __align__(16) float stage_all[kWarpsPerBlock][F::kStage];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float* st = stage_all[wib];
+  const int64_t S = (int64_t)p.n_win * p.T;
+  const int64_t n_groups = (S + 3) >> 2;
+  const int n_out[6] = {F::kBody * 2, F::kBody, 42, 21, 42, 21};
+
+  for (int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + wib; g < n_groups; g += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int64_t s0 = g << 2;
+    // ---- window index math (bit-exact integer work) ----
+    int64_t srcf[4];
+    bool consecutive = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int64_t s = s0 + i;
+      if (s < S) {
+        int64_t w = s / p.T;
+        int t = (int)(s - w * p.T);
+        int64_t start = p.win_start[w];
+        int64_t f = start + t;                        // crop [start, start+T)   text_pose_dataset.py:66-68
+        if (f >= p.n_frames || f < 0)                 // past the clip end -> pad rule
+          f = (p.pad_mode == B2H_PAD_REPEAT_FIRST && start >= 0 && start < p.n_frames) ? start : -1;  // :512-518 / :616-622
+        srcf[i] = f;
+        if (t == 0 && lane == 0 && p.n_frames_out) {
+          int64_t rem = p.n_frames - start;
+          p.n_frames_out[w] = rem < 0 ? 0 : (rem < p.T ? rem : (int64_t)p.T);   // :447
+        }
+      } else {
+        srcf[i] = -1;
+      }
+      if (i > 0 && srcf[i] != srcf[0] + i) consecutive = false;
+    }
+    const bool fast = p.aligned && consecutive && srcf[0] >= 0 && (srcf[0] & 3) == 0 && (s0 + 3 < S);
+    __syncwarp();
+    // ---- stage 4 source frames in shared memory ----
+    if (fast) {
+#pragma unroll
+      for (int a = 0; a < F::kSrc; ++a) {
+        const int len = F::src_len(a);                 // floats per frame; 4*len floats = len float4
+        const float4* gsrc = reinterpret_cast<const float4*>(p.src[a] + srcf[0] * len);
+        float4* sdst = reinterpret_cast<float4*>(st + F::src_off(a));
+        for (int q = lane; q < len; q += 32) sdst[q] = __ldcs(gsrc + q);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int a = 0; a < F::kSrc; ++a) {
+          const int len = F::src_len(a);
+          float* sdst = st + F::src_off(a) + i * len;
+          if (srcf[i] >= 0) {
+            const float* gsrc = p.src[a] + srcf[i] * len;
+            for (int q = lane; q < len; q += 32) sdst[q] = __ldcs(gsrc + q);
+          } else {
+            for (int q = lane; q < len; q += 32) sdst[q] = 0.0f;
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // ---- six output rows of the 4 slots ----
+    if (s0 + 3 < S) {
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        if (p.out[a] == nullptr) continue;
+        const int n = n_out[a];                       // floats per slot; 4 slots = n float4
+        float4* gdst = reinterpret_cast<float4*>(p.out[a] + s0 * n);
+        for (int q = lane; q < n; q += 32) {
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            int idx = q * 4 + e;
+            int i = idx / n, r = idx - i * n;
+            v[e] = out_elem<FMT>(st, a, i, r, p);
+          }
+          __stcs(gdst + q, make_float4(v[0], v[1], v[2], v[3]));
+        }
+      }
+      if (p.input_bf16) {  // bf16 copy of input_kp for the tensor-core net (no second pass over HBM)
+        const int n = F::kBody * 2;
+        for (int q = lane; q < n / 2; q += 32) {      // n*4 bf16 = n/2 x 16-B chunks
+          __nv_bfloat16 h[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            int idx = q * 8 + e;
+            int i = idx / n, r = idx - i * n;
+            h[e] = __float2bfloat16_rn(out_elem<FMT>(st, 0, i, r, p));
+          }
+          reinterpret_cast<uint4*>(p.input_bf16 + s0 * n)[q] = *reinterpret_cast<uint4*>(h);
+        }
+      }
+    } else {  // ragged tail (S % 4 != 0): scalar stores
+      const int nvalid = (int)(S - s0);
+      for (int a = 0; a < 6; ++a) {
+        if (p.out[a] == nullptr) continue;
+        const int n = n_out[a];
+        for (int idx = lane; idx < nvalid * n; idx += 32) {
+          int i = idx / n, r = idx - i * n;
+          p.out[a][s0 * n + idx] = out_elem<FMT>(st, a, i, r, p);
+        }
+      }
+      if (p.input_bf16) {
+        const int n = F::kBody * 2;
+        for (int idx = lane; idx < nvalid * n; idx += 32) {
+          int i = idx / n, r = idx - i * n;
+          p.input_bf16[s0 * n + idx] = __float2bfloat16_rn(out_elem<FMT>(st, 0, i, r, p));
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+
+template <int FMT>
+static int launch_pre(PreArgs& p, cudaStream_t stream) {
+  if (p.n_win <= 0 || p.T <= 0) return B2H_OK;
+  int64_t S = (int64_t)p.n_win * p.T;
+  int64_t groups = (S + 3) / 4;
+  int64_t blocks = (groups + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  int64_t cap = (int64_t)num_sms() * 8;            // 8 resident CTAs/SM, grid-stride beyond that
+  if (blocks > cap) blocks = cap;
+  preprocess_kernel<FMT><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(p);
+  count_launch();
+  return check_launch("preprocess_kernel");
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace b2h
+
+using namespace b2h;
+
+extern "C" int b2h_preprocess(const float* pose25, const float* hand_left, const float* hand_right, int64_t n_frames,
+                              const int64_t* win_start, int n_win, int T, int pad_mode, float factor,
+                              int dif_encoding, int normalize, float* input_kp, float* input_conf,
+                              float* target_kp, float* target_conf, float* left_kp, float* left_conf,
+                              int64_t* n_frames_out, void* input_kp_bf16, void* stream) {
+  if (!pose25 || !hand_left || !hand_right || !win_start || !input_kp || !input_conf || !target_kp || !target_conf) {
+    set_error("b2h_preprocess: null pointer");
+    return B2H_EINVAL;
+  }
+  if (pad_mode != B2H_PAD_REPEAT_FIRST && pad_mode != B2H_PAD_ZEROS) { set_error("b2h_preprocess: bad pad_mode %d", pad_mode); return B2H_EINVAL; }
+  if (n_frames < 0 || n_win < 0 || T < 0) { set_error("b2h_preprocess: negative size"); return B2H_ESHAPE; }
+  PreArgs p{};
+  p.src[0] = pose25; p.src[1] = hand_left; p.src[2] = hand_right;
+  p.n_frames = n_frames; p.win_start = win_start; p.n_win = n_win; p.T = T; p.pad_mode = pad_mode;
+  p.dif = dif_encoding; p.normalize = normalize; p.factor = factor;
+  p.out[0] = input_kp; p.out[1] = input_conf; p.out[2] = target_kp; p.out[3] = target_conf;
+  p.out[4] = left_kp; p.out[5] = left_conf;
+  p.n_frames_out = n_frames_out; p.input_bf16 = reinterpret_cast<__nv_bfloat16*>(input_kp_bf16);
+  bool al = aligned16(pose25) && aligned16(hand_left) && aligned16(hand_right) && aligned16(input_kp_bf16);
+  for (int a = 0; a < 6; ++a) al = al && aligned16(p.out[a]);
+  if (!al) { set_error("b2h_preprocess: pointers must be 16-byte aligned"); return B2H_EALIGN; }
+  p.aligned = 1;
+  return launch_pre<0>(p, (cudaStream_t)stream);
+}
+
+extern "C" int b2h_preprocess_h5(const float* rows150, int64_t n_frames, const int64_t* win_start, int n_win, int T,
+                                 int pad_mode, float factor, int dif_encoding, int normalize, float* input_kp,
+                                 float* input_conf, float* target_kp, float* target_conf, float* left_kp,
+                                 float* left_conf, int64_t* n_frames_out, void* stream) {
+  if (!rows150 || !win_start || !input_kp || !input_conf || !target_kp || !target_conf) {
+    set_error("b2h_preprocess_h5: null pointer");
+    return B2H_EINVAL;
+  }
+  if (pad_mode != B2H_PAD_REPEAT_FIRST && pad_mode != B2H_PAD_ZEROS) { set_error("b2h_preprocess_h5: bad pad_mode %d", pad_mode); return B2H_EINVAL; }
+  if (n_frames < 0 || n_win < 0 || T < 0) { set_error("b2h_preprocess_h5: negative size"); return B2H_ESHAPE; }
+  PreArgs p{};
+  p.src[0] = rows150; p.src[1] = nullptr; p.src[2] = nullptr;
+  p.n_frames = n_frames; p.win_start = win_start; p.n_win = n_win; p.T = T; p.pad_mode = pad_mode;
+  p.dif = dif_encoding; p.normalize = normalize; p.factor = factor;
+  p.out[0] = input_kp; p.out[1] = input_conf; p.out[2] = target_kp; p.out[3] = target_conf;
+  p.out[4] = left_kp; p.out[5] = left_conf;
+  p.n_frames_out = n_frames_out; p.input_bf16 = nullptr;
+  bool al = aligned16(rows150);
+  for (int a = 0; a < 6; ++a) al = al && aligned16(p.out[a]);
+  if (!al) { set_error("b2h_preprocess_h5: pointers must be 16-byte aligned"); return B2H_EALIGN; }
+  p.aligned = 1;
+  return launch_pre<1>(p, (cudaStream_t)stream);
+}

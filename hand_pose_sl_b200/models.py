@@ -1,0 +1,218 @@
+"""Drop-in for the reference's `models.ConvModel` (body2hand/src/models/HandPoseModels.py:17-84).
+
+Same constructor `ConvModel(conv_channels, activation, pos_emb)`, same parameter names and shapes
+(`conv{1..4}.{weight,bias}`, fp32, (Cout,Cin,5)), same `forward(inp: (B,T,K,2)) -> (B,T,21,2)`, same
+default initialisation under the same `torch.manual_seed` (the four nn.Conv1d are built in the
+reference's order).  Behind it: one fused CUDA launch per forward (libb2h.so via ctypes), the
+parameters being views of ONE flat fp32 buffer so the optimiser and the gradient all-reduce are
+single launches too.  Extra kwarg `precision` in {"fp32","bf16"} selects the FFMA kernel (1e-4 parity)
+or the tcgen05 kernel (bf16 operands, fp32 accumulation in TMEM, 2e-2 parity)."""
+from __future__ import annotations
+
+import weakref
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class LinearPositionalEmbedding(nn.Module):
+    """HandPoseModels.py:66-84.  The reference concatenates a constant row t/max_len in front of the
+    channels (and only works when T == max_len); here the row is generated inside the conv kernel."""
+
+    def __init__(self, max_len=100):
+        super().__init__()
+        self.max_len = max_len
+        self.pe = (torch.arange(max_len).float() / max_len)[None, None, :]
+
+
+class _ConvForward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, model, *params):
+        y = model._forward_impl(x)
+        ctx.model = model
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        (x,) = ctx.saved_tensors
+        model = ctx.model
+        grads = model._backward_impl(x, grad_y)
+        return (None, None) + tuple(grads)
+
+
+class ConvModel(nn.Module):
+    def __init__(self, conv_channels, activation, pos_emb, precision="fp32", n_keypoints=12):
+        super().__init__()
+        n_in = n_keypoints * 2
+        if pos_emb:
+            self.pos_emb = LinearPositionalEmbedding(max_len=100)                          # HandPoseModels.py:23
+            self.conv1 = nn.Conv1d(n_in + 1, conv_channels, kernel_size=5, padding=2)      # :24
+        else:
+            self.pos_emb = None
+            self.conv1 = nn.Conv1d(n_in, conv_channels, kernel_size=5, padding=2)          # :28
+        self.conv2 = nn.Conv1d(conv_channels, conv_channels, kernel_size=5, padding=2)     # :30
+        self.conv3 = nn.Conv1d(conv_channels, conv_channels, kernel_size=5, padding=2)     # :31
+        self.conv4 = nn.Conv1d(conv_channels, 2 * 21, kernel_size=5, padding=2)            # :32
+        if activation == "ReLU":
+            self.activation = nn.ReLU()                                                     # :34-35
+        else:
+            raise ValueError()                                                              # :37
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        self.precision = precision
+        self.conv_channels = int(conv_channels)
+        self.n_in = n_in
+        self._flat = None
+        self._packed = None
+        self._packed_versions = None
+        self._workspace = None
+        self._flatten()
+
+    # ------------------------------------------------------------------ flat parameter storage
+    def _ordered_params(self):
+        return [self.conv1.weight, self.conv1.bias, self.conv2.weight, self.conv2.bias,
+                self.conv3.weight, self.conv3.bias, self.conv4.weight, self.conv4.bias]
+
+    def _flatten(self):
+        """Make the 8 parameters views of one contiguous fp32 buffer (state_dict order)."""
+        ps = self._ordered_params()
+        dev = ps[0].device
+        flat = torch.empty(sum(p.numel() for p in ps), dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in ps:
+                n = p.numel()
+                flat[off:off + n].copy_(p.detach().reshape(-1).to(torch.float32))
+                p.data = flat[off:off + n].view(p.shape)
+                p._b2h_owner = weakref.ref(self)
+                off += n
+        self._flat = flat
+        self._packed = None
+        self._packed_versions = None
+        self._workspace = None
+
+    def _is_flat(self):
+        if self._flat is None:
+            return False
+        base, off = self._flat.data_ptr(), 0
+        for p in self._ordered_params():
+            if p.data_ptr() != base + off * 4 or p.dtype != torch.float32 or not p.is_contiguous():
+                return False
+            off += p.numel()
+        return True
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)    # .to()/.cuda()/.float(): moves every param on its own
+        self._flatten()
+        return out
+
+    def flat_parameters(self):
+        if not self._is_flat():
+            self._flatten()
+        return self._flat
+
+    def mark_packed_stale(self):
+        self._packed_versions = None
+
+    def _geometry(self):
+        return self.n_in, self.conv_channels, 1 if self.pos_emb is not None else 0
+
+    def packed_weights(self, fresh_from_kernel=False):
+        """Extension-owned operand layouts (fp32 tap-major + bf16 UMMA blocks), rebuilt lazily when any
+        parameter's version counter moved (load_state_dict, a stock torch optimiser, manual edits)."""
+        flat = self.flat_parameters()
+        _lib.require_device(flat, "ConvModel parameters")
+        n_in, C, pe = self._geometry()
+        if self._packed is None or self._packed.device != flat.device:
+            self._packed = torch.zeros(_lib.packed_bytes(n_in, C, pe), dtype=torch.uint8, device=flat.device)
+            self._packed_versions = None
+        versions = tuple(p._version for p in self._ordered_params())
+        if fresh_from_kernel:
+            self._packed_versions = versions
+        elif self._packed_versions != versions:
+            lib = _lib.load()
+            _lib.check(lib.b2h_pack_weights(_lib.ptr(flat), _lib.ptr(self._packed), n_in, C, pe, _lib.stream_ptr(flat.device)))
+            self._packed_versions = versions
+        return self._packed
+
+    def workspace(self, B, T):
+        n_in, C, pe = self._geometry()
+        need = _lib.workspace_bytes(B, T, n_in, C, pe, _lib.PRECISIONS[self.precision])
+        dev = self._flat.device
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+        return self._workspace
+
+    # ------------------------------------------------------------------ kernels
+    def _check_input(self, inp):
+        _lib.require_device(inp, "ConvModel input")
+        _lib.require_sm100(inp.device)
+        if inp.dim() != 4:
+            raise RuntimeError(f"ConvModel expects (B, T, K, 2), got {tuple(inp.shape)}")
+        B, T, K, D = inp.shape
+        if K * D != self.n_in:
+            # the reference fails inside conv1 with a channel-mismatch RuntimeError
+            raise RuntimeError(f"expected input with {self.n_in} channels (K*2), got {K * D} channels instead")
+        if self.pos_emb is not None and T != self.pos_emb.max_len:
+            # torch.cat in LinearPositionalEmbedding.forward fails unless T == max_len (HandPoseModels.py:82)
+            raise RuntimeError(f"Sizes of tensors must match: pos_emb requires T == {self.pos_emb.max_len}, got {T}")
+        if inp.dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError(f"ConvModel input must be float32 or bfloat16, got {inp.dtype}")
+        if self._flat.device != inp.device:
+            raise RuntimeError(f"input is on {inp.device} but the model is on {self._flat.device}")
+        return B, T
+
+    def _forward_impl(self, inp, lengths=None, out_scale=1.0):
+        B, T = self._check_input(inp)
+        x = inp.contiguous()
+        n_in, C, pe = self._geometry()
+        packed = self.packed_weights()
+        y = torch.empty((B, T, 21, 2), dtype=torch.float32, device=x.device)
+        lib = _lib.load()
+        len32 = None
+        if lengths is not None:
+            len32 = torch.as_tensor(lengths).to(device=x.device, dtype=torch.int32, non_blocking=True).contiguous()
+        _lib.check(lib.b2h_conv_forward(_lib.ptr(x), _lib.DT_BF16 if x.dtype == torch.bfloat16 else _lib.DT_F32,
+                                        _lib.ptr(self._flat), _lib.ptr(packed), _lib.ptr(len32), _lib.ptr(y), B, T,
+                                        n_in, C, pe, _lib.PRECISIONS[self.precision], 1 if len32 is not None else 0,
+                                        float(out_scale), _lib.stream_ptr(x.device)))
+        return y
+
+    def _backward_impl(self, x, grad_y):
+        B, T = x.shape[0], x.shape[1]
+        xc = x.contiguous()
+        gy = grad_y.to(torch.float32).contiguous().view(B, T, 42)
+        n_in, C, pe = self._geometry()
+        packed = self.packed_weights()
+        ws = self.workspace(B, T)
+        grads = torch.empty_like(self._flat)
+        lib = _lib.load()
+        _lib.check(lib.b2h_conv_backward(_lib.ptr(xc), _lib.DT_BF16 if xc.dtype == torch.bfloat16 else _lib.DT_F32,
+                                         _lib.ptr(gy), _lib.ptr(self._flat), _lib.ptr(packed), _lib.ptr(grads), B, T,
+                                         n_in, C, pe, _lib.PRECISIONS[self.precision], _lib.ptr(ws), ws.numel(),
+                                         _lib.stream_ptr(xc.device)))
+        out, off = [], 0
+        for p in self._ordered_params():
+            out.append(grads[off:off + p.numel()].view(p.shape))
+            off += p.numel()
+        return out
+
+    def forward(self, inp):
+        """inp (B,T,K,2) -> (B,T,21,2)   HandPoseModels.py:40-64.  (The reference returns a permuted
+        view of a (B,42,T) tensor; this returns the same values contiguous.)"""
+        if not self._is_flat():
+            self._flatten()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self._ordered_params()):
+            return _ConvForward.apply(inp, self, *self._ordered_params())
+        return self._forward_impl(inp)
+
+    @torch.no_grad()
+    def predict(self, inp, lengths=None, denormalize=None):
+        """Inference helper: forward with the optional fused epilogues -- mask_output(lengths)
+        (steps/utils.py:309-312) and `prediction *= 1280` (steps/traintest.py:270-271)."""
+        if not self._is_flat():
+            self._flatten()
+        return self._forward_impl(inp, lengths=lengths, out_scale=1.0 if denormalize is None else float(denormalize))

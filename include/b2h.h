@@ -1,0 +1,163 @@
+/* b2h.h -- C-ABI of libb2h.so: the B200 (sm_100a) hot path of body2hand.
+ *
+ * The reference (benoriol/hand_pose_sl) has no FFI of its own: its hot path sits behind the PyTorch
+ * Python API.  Each entry point below replaces the work one reference call does and cites it
+ * (paths relative to the reference root).  All pointers are DEVICE pointers owned by the caller
+ * (torch allocator) unless the name ends in _host; kernels are enqueued on `stream` (a cudaStream_t
+ * passed as void*), never allocate, never synchronise, never free -> CUDA-graph capturable.
+ * Return value: 0 on success, negative B2H_E* otherwise; b2h_last_error() holds a message
+ * (thread-local).  Nothing here throws or exits.
+ */
+#ifndef B2H_H_
+#define B2H_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2H_OK        0
+#define B2H_EINVAL   -1   /* null pointer / bad enum */
+#define B2H_ESHAPE   -2   /* unsupported shape (C, T, channel count) */
+#define B2H_EALIGN   -3   /* pointer not aligned as required */
+#define B2H_EARCH    -4   /* device is not sm_100 */
+#define B2H_ECUDA    -5   /* CUDA launch error (cudaGetLastError after enqueue) */
+#define B2H_EWORKSPACE -6 /* workspace too small */
+
+/* precision modes (north_star: fp32 mode 1e-4, bf16 mode 2e-2) */
+#define B2H_FP32 0        /* FFMA, fp32 accumulate everywhere                         */
+#define B2H_BF16 1        /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate (TMEM) */
+
+/* loss kinds -- only the two the reference actually computes (steps/traintest.py:114-117) */
+#define B2H_LOSS_L1     0 /* maskedPoseL1     steps/utils.py:413-428 (batch mean) */
+#define B2H_LOSS_CONFL1 1 /* poderatedPoseL1  steps/utils.py:431-452 (batch SUM)  */
+
+/* pad rule of a cropped window */
+#define B2H_PAD_REPEAT_FIRST 0  /* dataloaders/text_pose_dataset.py:511-518 (JSON datasets) */
+#define B2H_PAD_ZEROS        1  /* dataloaders/text_pose_dataset.py:614-622 (H5 dataset)    */
+
+/* element types of activation tensors crossing the ABI */
+#define B2H_DT_F32  0
+#define B2H_DT_BF16 1
+
+const char* b2h_last_error(void);
+int b2h_version(void);
+/* 1 if the current device is compute capability 10.x, else 0 (no CPU fallback exists). */
+int b2h_device_ok(void);
+
+/* ---- model geometry ------------------------------------------------------------------------
+ * ConvModel.__init__  body2hand/src/models/HandPoseModels.py:18-37:
+ * conv1 (C, n_in[+1 if pos_emb], 5), conv2/3 (C, C, 5), conv4 (42, C, 5) + biases; the flat fp32
+ * parameter buffer holds them in state_dict order conv1.weight, conv1.bias, ..., conv4.bias. */
+int64_t b2h_param_count(int n_in, int C, int pos_emb);
+/* float offset of conv{layer}.weight (is_bias=0) / .bias (is_bias=1) in the flat buffer, layer 1..4 */
+int64_t b2h_param_offset(int n_in, int C, int pos_emb, int layer, int is_bias);
+/* bytes of the extension-owned packed weight buffer (fp32 tap-major + bf16 UMMA operand layouts) */
+int64_t b2h_packed_bytes(int n_in, int C, int pos_emb);
+/* bytes of scratch the train entry points need (per-CTA gradient partials for a deterministic
+ * two-stage reduction + loss partials) */
+int64_t b2h_workspace_bytes(int B, int T, int n_in, int C, int pos_emb, int precision);
+/* 1 if (T, C) is supported by the given precision's kernels on this build, else 0 */
+int b2h_supported(int T, int n_in, int C, int pos_emb, int precision);
+
+/* Re-layout the flat fp32 parameters into the packed buffer (run after load_state_dict / any
+ * out-of-band weight change; the fused Adam keeps it fresh by itself). */
+int b2h_pack_weights(const float* params, void* packed, int n_in, int C, int pos_emb, void* stream);
+
+/* ---- K0 preprocessing -----------------------------------------------------------------------
+ * Replaces, per window slot: load_keypoints + BODY_HEAD_KEYPOINTS gather
+ * (dataloaders/text_pose_dataset.py:14-50), crop/pad/clip (…:52-68, 511-529), .float() (…:536-544),
+ * WristDifference / ChestDifference / NormalizeFixedFactor / BuildRightHandItem
+ * (steps/utils.py:180-210, 261-277).  Bit-exact (IEEE sub.rn then div.rn).
+ * Inputs: OpenPose rows [x,y,c]: pose25 (F,25,3), hand_left (F,21,3), hand_right (F,21,3) fp32.
+ * Window w covers source frames [win_start[w], win_start[w]+T) cut at F, padded by `pad_mode`.
+ * Outputs (W,T,12,2) (W,T,12) (W,T,21,2) (W,T,21) [(W,T,21,2) (W,T,21) nullable] fp32,
+ * n_frames_out (W) int64 = min(F - start, T)  (…:447);  input_kp_bf16 nullable (W,T,24) bf16 copy
+ * feeding the bf16 net without a second pass. */
+int b2h_preprocess(const float* pose25, const float* hand_left, const float* hand_right, int64_t n_frames,
+                   const int64_t* win_start, int n_win, int T, int pad_mode, float factor, int dif_encoding,
+                   int normalize, float* input_kp, float* input_conf, float* target_kp, float* target_conf,
+                   float* left_kp, float* left_conf, int64_t* n_frames_out, void* input_kp_bf16, void* stream);
+
+/* Same for the packed H5 row format of TextPoseH5Dataset.array2item
+ * (dataloaders/text_pose_dataset.py:587-612): rows (F,150) = [x0..x49 | y0..y49 | c0..c49],
+ * body = columns 0..7 (8 keypoints), left hand 8..28, right hand 29..49.  Outputs (W,T,8,2) (W,T,8) ... */
+int b2h_preprocess_h5(const float* rows150, int64_t n_frames, const int64_t* win_start, int n_win, int T,
+                      int pad_mode, float factor, int dif_encoding, int normalize, float* input_kp,
+                      float* input_conf, float* target_kp, float* target_conf, float* left_kp, float* left_conf,
+                      int64_t* n_frames_out, void* stream);
+
+/* ---- K1 forward -----------------------------------------------------------------------------
+ * ConvModel.forward  models/HandPoseModels.py:40-64 (+ LinearPositionalEmbedding :66-84 when
+ * pos_emb).  x (B,T,n_in) NWC [== the reference's (B,T,12,2)], x_dtype fp32 or bf16;
+ * y (B,T,42) fp32 [== (B,T,21,2)].  lengths nullable int32 (B): when apply_mask, rows t>=len are
+ * written as 0 (mask_output, steps/utils.py:309-312).  out_scale multiplies the result
+ * (1280 = the de-normalise of steps/traintest.py:270-271; 1 = none). */
+int b2h_conv_forward(const void* x, int x_dtype, const float* params, const void* packed, const int32_t* lengths,
+                     float* y, int B, int T, int n_in, int C, int pos_emb, int precision, int apply_mask,
+                     float out_scale, void* stream);
+
+/* ---- K2 fused forward + loss + backward --------------------------------------------------------
+ * One iteration of steps/traintest.py:94-120 up to loss.backward():  forward, mask_output,
+ * maskedPoseL1 / poderatedPoseL1, and every parameter gradient (conv dgrad/wgrad/bias-grad, ReLU
+ * mask).  grads_out: flat fp32 (b2h_param_count), overwritten.  loss_out: 1 float.
+ * pred_out nullable (B,T,42) masked prediction.  conf (B,T,21) only for B2H_LOSS_CONFL1. */
+int b2h_train_forward_backward(const void* x, int x_dtype, const float* target, const float* conf,
+                               const int32_t* lengths, const float* params, const void* packed,
+                               float* grads_out, float* loss_out, float* pred_out, int B, int T, int n_in, int C,
+                               int pos_emb, int loss_kind, int precision, void* workspace,
+                               int64_t workspace_bytes, void* stream);
+
+/* Backward of ConvModel.forward alone for the modular autograd path (what loss.backward() does
+ * below the criterion, steps/traintest.py:120): d_y (B,T,42) fp32 -> flat parameter gradients
+ * (activations are recomputed in shared memory, nothing was saved by the forward). */
+int b2h_conv_backward(const void* x, int x_dtype, const float* d_y, const float* params, const void* packed,
+                      float* grads_out, int B, int T, int n_in, int C, int pos_emb, int precision,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- criteria as stand-alone calls (modular API) ------------------------------------------------
+ * mask_output  steps/utils.py:309-312 (in place). */
+int b2h_mask_output(float* y, const int32_t* lengths, int B, int T, int row_elems, void* stream);
+/* maskedPoseL1 / poderatedPoseL1 forward value and d(loss)/d(pred) in one pass
+ * (steps/utils.py:413-452).  pred/target (B,T,row_elems), scores (B,T,row_elems/2) nullable,
+ * loss_out 1 float, d_pred nullable (B,T,row_elems), row_scratch (B) floats. */
+int b2h_pose_l1(const float* pred, const float* target, const float* scores, const int32_t* lengths, int B,
+                int T, int row_elems, int loss_kind, float* loss_out, float* d_pred, float* row_scratch,
+                void* stream);
+
+/* ---- K3 fused Adam ------------------------------------------------------------------------------
+ * torch.optim.Adam.step with torch defaults (steps/traintest.py:48,121) over the flat buffer:
+ * g = grads*grad_scale (grad_scale = 1/world for data parallel); m,v,p updated in place; when
+ * `packed` is non-null the new weights are also scattered into the packed operand layouts so the
+ * next forward needs no re-pack.  step is 1-based. */
+int b2h_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                  double beta1, double beta2, double eps, int64_t step, float grad_scale, void* packed,
+                  int n_in, int C, int pos_emb, void* stream);
+
+/* Fast path = b2h_train_forward_backward + b2h_adam_step with the cross-CTA gradient reduction
+ * fused into the Adam kernel (2 launches per step, zero host work). */
+int b2h_train_step(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,
+                   float* params, void* packed, float* exp_avg, float* exp_avg_sq, float* loss_out, int B, int T,
+                   int n_in, int C, int pos_emb, int loss_kind, int precision, double lr, double beta1,
+                   double beta2, double eps, int64_t step, void* workspace, int64_t workspace_bytes,
+                   void* stream);
+
+/* tcgen05 / TMEM / descriptor self-test (tests/test_tc_probe.py): D = A·B^T for one 128xNx(16*ksteps)
+ * bf16 tile staged in the no-swizzle K-major layout the conv kernels use, A rows shifted by `shift`
+ * rows (the implicit-im2col trick).  out (128,N) fp32. */
+int b2h_tc_probe(const void* a_bf16, const void* b_bf16, float* out, int n, int ksteps, int shift, int variant,
+                 void* stream);
+
+/* device-side wait-timeout status of the tensor-core kernels: 0 = clean, else the id of the wait that
+ * gave up (the kernels never spin forever); reading clears it.  Synchronises the device. */
+int b2h_tc_status(void);
+
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t b2h_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2H_H_ */
