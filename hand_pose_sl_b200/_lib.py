@@ -40,17 +40,17 @@ _SIGNATURES = {
                                  c_int, c_int, c_int, c_float, c_void_p]),
     "b2h_train_forward_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
-                                           c_int64, c_void_p]),
+                                           c_void_p, c_int64, c_void_p]),
     "b2h_conv_backward": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_void_p, c_int64, c_void_p]),
     "b2h_mask_output": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2h_pose_l1": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                             c_void_p, c_void_p]),
     "b2h_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double,
-                              c_int64, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+                              c_int64, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2h_train_step": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
-                               c_double, c_int64, c_void_p, c_int64, c_void_p]),
+                               c_double, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2h_tc_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b2h_tc_status": (c_int, []),
     "b2h_launch_count": (c_int64, []),

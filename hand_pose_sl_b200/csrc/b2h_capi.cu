@@ -124,7 +124,7 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
                         const int32_t* lengths, const float* params, const void* packed, float* pred_out, int B, int T,
                         int n_in, int C, int pos_emb, int loss_kind, int precision, int mode, void* workspace,
                         int64_t workspace_bytes, cudaStream_t stream, Geo& g, int& nparts, float*& partials,
-                        float*& loss_partials, const char* who) {
+                        float*& loss_partials, const char* who, long long* step_dev = nullptr) {
   if (!x || !params || !packed || !workspace) { set_error("%s: null pointer", who); return B2H_EINVAL; }
   if (x_dtype != B2H_DT_F32 && x_dtype != B2H_DT_BF16) { set_error("%s: bad x_dtype %d", who, x_dtype); return B2H_EINVAL; }
   if (!geo_ok(n_in, C, pos_emb, who)) return B2H_ESHAPE;
@@ -147,20 +147,21 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
   a.x = x; a.x_dtype = x_dtype; a.target = target; a.conf = conf; a.d_y = d_y; a.lengths = lengths; a.params = params;
   a.packed = reinterpret_cast<const char*>(packed); a.y = pred_out; a.partials = partials; a.loss_partials = loss_partials;
   a.B = B; a.T = T; a.loss_kind = loss_kind; a.apply_mask = 1; a.mode = mode; a.out_scale = 1.0f; a.geo = g;
+  a.step_dev = step_dev;
   return launch_fp32(a, true, stream, nparts);
 }
 
 extern "C" int b2h_train_forward_backward(const void* x, int x_dtype, const float* target, const float* conf,
                                           const int32_t* lengths, const float* params, const void* packed,
                                           float* grads_out, float* loss_out, float* pred_out, int B, int T, int n_in,
-                                          int C, int pos_emb, int loss_kind, int precision, void* workspace,
-                                          int64_t workspace_bytes, void* stream) {
-  if (!grads_out || !loss_out) { set_error("b2h_train_forward_backward: null output"); return B2H_EINVAL; }
+                                          int C, int pos_emb, int loss_kind, int precision, int64_t* step_dev,
+                                          void* workspace, int64_t workspace_bytes, void* stream) {
+  if (grads_out && !loss_out) { set_error("b2h_train_forward_backward: null loss_out"); return B2H_EINVAL; }
   Geo g; int nparts; float *partials, *loss_partials;
   int rc = train_common(x, x_dtype, target, conf, nullptr, lengths, params, packed, pred_out, B, T, n_in, C, pos_emb,
                         loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
-                        loss_partials, "b2h_train_forward_backward");
-  if (rc) return rc;
+                        loss_partials, "b2h_train_forward_backward", reinterpret_cast<long long*>(step_dev));
+  if (rc || !grads_out) return rc;   // grads_out == NULL: only the fused kernel runs, partials stay in the workspace
   return launch_reduce(partials, nparts, g.P, grads_out, loss_partials, loss_out, (cudaStream_t)stream);
 }
 
@@ -179,24 +180,25 @@ extern "C" int b2h_conv_backward(const void* x, int x_dtype, const float* d_y, c
 extern "C" int b2h_train_step(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,
                               float* params, void* packed, float* exp_avg, float* exp_avg_sq, float* loss_out, int B,
                               int T, int n_in, int C, int pos_emb, int loss_kind, int precision, double lr, double beta1,
-                              double beta2, double eps, int64_t step, void* workspace, int64_t workspace_bytes,
-                              void* stream) {
+                              double beta2, double eps, int64_t step, int64_t* step_dev, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
   if (!exp_avg || !exp_avg_sq || !loss_out) { set_error("b2h_train_step: null pointer"); return B2H_EINVAL; }
-  if (step < 1) { set_error("b2h_train_step: step must be >= 1"); return B2H_EINVAL; }
+  if (step < 1 && !step_dev) { set_error("b2h_train_step: step must be >= 1"); return B2H_EINVAL; }
   Geo g; int nparts; float *partials, *loss_partials;
   int rc = train_common(x, x_dtype, target, conf, nullptr, lengths, params, packed, nullptr, B, T, n_in, C, pos_emb,
                         loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
-                        loss_partials, "b2h_train_step");
+                        loss_partials, "b2h_train_step", reinterpret_cast<long long*>(step_dev));
   if (rc) return rc;
-  return launch_adam(params, partials, nparts, exp_avg, exp_avg_sq, g.P, lr, beta1, beta2, eps, step, 1.0f, packed, g,
+  return launch_adam(params, partials, nparts, exp_avg, exp_avg_sq, g.P, lr, beta1, beta2, eps, step < 1 ? 1 : step,
+                     reinterpret_cast<const long long*>(step_dev), 1.0f, packed, g,
                      loss_partials, loss_out, (cudaStream_t)stream);
 }
 
 extern "C" int b2h_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
-                             double beta1, double beta2, double eps, int64_t step, float grad_scale, void* packed,
-                             int n_in, int C, int pos_emb, void* stream) {
+                             double beta1, double beta2, double eps, int64_t step, const int64_t* step_dev,
+                             float grad_scale, void* packed, int n_in, int C, int pos_emb, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq) { set_error("b2h_adam_step: null pointer"); return B2H_EINVAL; }
-  if (step < 1 || n < 0) { set_error("b2h_adam_step: bad step/n"); return B2H_EINVAL; }
+  if ((step < 1 && !step_dev) || n < 0) { set_error("b2h_adam_step: bad step/n"); return B2H_EINVAL; }
   Geo g{};
   if (packed) {
     if (!geo_ok(n_in, C, pos_emb, "b2h_adam_step")) return B2H_ESHAPE;
@@ -204,8 +206,8 @@ extern "C" int b2h_adam_step(float* params, const float* grads, float* exp_avg, 
     if (g.P != n) { set_error("b2h_adam_step: n=%lld does not match geometry (%d)", (long long)n, g.P); return B2H_ESHAPE; }
   }
   if (n == 0) return B2H_OK;
-  return launch_adam(params, grads, 1, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, packed, g, nullptr,
-                     nullptr, (cudaStream_t)stream);
+  return launch_adam(params, grads, 1, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step < 1 ? 1 : step,
+                     reinterpret_cast<const long long*>(step_dev), grad_scale, packed, g, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int b2h_mask_output(float* y, const int32_t* lengths, int B, int T, int row_elems, void* stream) {

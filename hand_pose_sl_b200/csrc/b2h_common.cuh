@@ -79,6 +79,7 @@ struct Fp32Args {
   float* y;                 // forward output / masked prediction (nullable in train mode)
   float* partials;          // [grid][P]
   float* loss_partials;     // [grid]
+  long long* step_dev;      // nullable: device step counter, incremented by block 0 (read by the Adam kernel)
   int B, T, loss_kind, apply_mask, mode;   // mode 0 = forward, 1 = train (loss inside), 2 = backward of given d_y
   float out_scale;
   Geo geo;
@@ -103,8 +104,8 @@ int tc_status_and_clear();
 int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t stream);
 int launch_reduce(const float* partials, int nparts, int P, float* grads, const float* loss_partials, float* loss_out, cudaStream_t stream);
 int launch_adam(float* params, const float* grads, int nparts, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
-                double eps, int64_t step, float grad_scale, void* packed, const Geo& g, const float* loss_partials, float* loss_out,
-                cudaStream_t stream);
+                double eps, int64_t step, const long long* step_dev, float grad_scale, void* packed, const Geo& g,
+                const float* loss_partials, float* loss_out, cudaStream_t stream);
 int launch_mask_output(float* y, const int32_t* lengths, int B, int T, int row, cudaStream_t stream);
 int launch_pose_l1(const float* pred, const float* target, const float* scores, const int32_t* lengths, int B, int T, int row,
                    int loss_kind, float* loss_out, float* d_pred, float* row_scratch, cudaStream_t stream);

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kThreads) conv_fp32_kernel(Fp32Args p) {
     Wd[l] = reinterpret_cast<const float*>(p.packed + g.wd_off[l]);
     bias[l] = p.params + g.b_off[l];
   }
+  if (TRAIN && p.step_dev && blockIdx.x == 0 && threadIdx.x == 0) *p.step_dev += 1;
   float* part = TRAIN ? p.partials + (size_t)blockIdx.x * g.P : nullptr;
   float loss_acc = 0.0f;
   bool first = true;

@@ -59,6 +59,8 @@ struct AdamArgs {
   float* params; const float* grads; int nparts; int64_t n;
   float* m; float* v;
   float beta1, beta2, one_minus_b1, one_minus_b2, step_size, inv_bc2_sqrt, eps, grad_scale;
+  double lr_d, beta1_d, beta2_d;
+  const long long* step_dev;
   char* packed; Geo g;
   const float* loss_partials; float* loss_out;
 };
@@ -68,6 +70,17 @@ struct AdamArgs {
 //   denom = v.sqrt()/sqrt(1-b2^t) + eps;  p.addcdiv_(m, denom, value=-lr/(1-b1^t))
 __global__ void adam_kernel(AdamArgs a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float s_step_size, s_inv_bc2_sqrt;
+  if (a.step_dev) {   // bias corrections from the device-side step counter (graph replay)
+    if (threadIdx.x == 0) {
+      const double t = (double)*a.step_dev;
+      s_step_size = (float)(a.lr_d / (1.0 - pow(a.beta1_d, t)));
+      s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(a.beta2_d, t)));
+    }
+    __syncthreads();
+    a.step_size = s_step_size;
+    a.inv_bc2_sqrt = s_inv_bc2_sqrt;
+  }
   if (i < a.n) {
     float gr = 0.f;
     for (int c = 0; c < a.nparts; ++c) gr += a.grads[(size_t)c * a.n + i];
@@ -163,7 +176,7 @@ int launch_reduce(const float* partials, int nparts, int P, float* grads, const 
 }
 
 int launch_adam(float* params, const float* grads, int nparts, float* m, float* v, int64_t n, double lr, double beta1,
-                double beta2, double eps, int64_t step, float grad_scale, void* packed, const Geo& g,
+                double beta2, double eps, int64_t step, const long long* step_dev, float grad_scale, void* packed, const Geo& g,
                 const float* loss_partials, float* loss_out, cudaStream_t stream) {
   AdamArgs a;
   a.params = params; a.grads = grads; a.nparts = nparts; a.n = n; a.m = m; a.v = v;
@@ -175,6 +188,7 @@ int launch_adam(float* params, const float* grads, int nparts, float* m, float* 
   a.eps = (float)eps; a.grad_scale = grad_scale;
   a.packed = reinterpret_cast<char*>(packed); a.g = g;
   a.loss_partials = loss_partials; a.loss_out = loss_out;
+  a.lr_d = lr; a.beta1_d = beta1; a.beta2_d = beta2; a.step_dev = step_dev;
   adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a);
   count_launch();
   return check_launch("adam_kernel");

@@ -16,6 +16,13 @@ import torch.nn as nn
 
 from . import _lib
 
+_OWNERS = weakref.WeakValueDictionary()   # id(model) -> model, looked up through Parameter._b2h_owner_id
+
+
+def owner_of(param):
+    """The ConvModel whose flat buffer `param` is a view of (None if it is not one of ours)."""
+    return _OWNERS.get(getattr(param, "_b2h_owner_id", None))
+
 
 class LinearPositionalEmbedding(nn.Module):
     """HandPoseModels.py:66-84.  The reference concatenates a constant row t/max_len in front of the
@@ -87,12 +94,23 @@ class ConvModel(nn.Module):
                 n = p.numel()
                 flat[off:off + n].copy_(p.detach().reshape(-1).to(torch.float32))
                 p.data = flat[off:off + n].view(p.shape)
-                p._b2h_owner = weakref.ref(self)
+                p._b2h_owner_id = id(self)
                 off += n
+        _OWNERS[id(self)] = self
         self._flat = flat
         self._packed = None
         self._packed_versions = None
         self._workspace = None
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        for k in ("_flat", "_packed", "_packed_versions", "_workspace"):
+            st[k] = None
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._flatten()
 
     def _is_flat(self):
         if self._flat is None:

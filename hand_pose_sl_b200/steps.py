@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .models import ConvModel
+from .models import ConvModel, owner_of
 
 
 def _lengths_i32(lengths, device, B):
@@ -149,8 +149,7 @@ class FusedAdam(torch.optim.Optimizer):
 
     def _owner(self, group):
         ps = group["params"]
-        owner = getattr(ps[0], "_b2h_owner", None)
-        model = owner() if owner is not None else None
+        model = owner_of(ps[0])
         if model is None or len(ps) != 8:
             return None
         if not model._is_flat():
@@ -215,7 +214,7 @@ class FusedAdam(torch.optim.Optimizer):
                 packed = model.packed_weights()
                 _lib.check(lib.b2h_adam_step(_lib.ptr(flat), _lib.ptr(fg), _lib.ptr(st["m"]), _lib.ptr(st["v"]),
                                              flat.numel(), float(group["lr"]), b1, b2, group["eps"], st["step"],
-                                             float(grad_scale), _lib.ptr(packed), n_in, C, pe,
+                                             None, float(grad_scale), _lib.ptr(packed), n_in, C, pe,
                                              _lib.stream_ptr(flat.device)))
                 model.packed_weights(fresh_from_kernel=True)
                 for p in group["params"]:
@@ -234,10 +233,10 @@ class FusedAdam(torch.optim.Optimizer):
                     g = p.grad.contiguous()
                     _lib.check(lib.b2h_adam_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(s["exp_avg"]), _lib.ptr(s["exp_avg_sq"]),
                                                  p.numel(), float(group["lr"]), b1, b2, group["eps"], int(s["step"]),
-                                                 float(grad_scale), None, 0, 0, 0, _lib.stream_ptr(p.device)))
-                    owner = getattr(p, "_b2h_owner", None)
-                    if owner is not None and owner() is not None:
-                        owner().mark_packed_stale()
+                                                 None, float(grad_scale), None, 0, 0, 0, _lib.stream_ptr(p.device)))
+                    owner = owner_of(p)
+                    if owner is not None:
+                        owner.mark_packed_stale()
         return loss
 
 
@@ -271,7 +270,7 @@ def fused_train_step(model: ConvModel, batch, optimizer: FusedAdam, loss="L1"):
                                   _lib.ptr(conf), _lib.ptr(len32), _lib.ptr(flat), _lib.ptr(packed), _lib.ptr(st["m"]),
                                   _lib.ptr(st["v"]), _lib.ptr(loss_out), B, T, n_in, C, pe, kind,
                                   _lib.PRECISIONS[model.precision], float(group["lr"]), b1, b2, group["eps"], st["step"],
-                                  _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+                                  None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
     model.packed_weights(fresh_from_kernel=True)
     return loss_out
 
@@ -298,8 +297,8 @@ def forward_backward(model: ConvModel, batch, loss="L1", want_pred=False):
     _lib.check(lib.b2h_train_forward_backward(_lib.ptr(x), _lib.DT_BF16 if x.dtype == torch.bfloat16 else _lib.DT_F32,
                                               _lib.ptr(tgt), _lib.ptr(conf), _lib.ptr(len32), _lib.ptr(flat),
                                               _lib.ptr(packed), _lib.ptr(grads), _lib.ptr(loss_out), _lib.ptr(pred), B, T,
-                                              n_in, C, pe, kind, _lib.PRECISIONS[model.precision], _lib.ptr(ws),
-                                              ws.numel(), _lib.stream_ptr(dev)))
+                                              n_in, C, pe, kind, _lib.PRECISIONS[model.precision], None,
+                                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
     return (loss_out, grads, pred) if want_pred else (loss_out, grads)
 
 

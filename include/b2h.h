@@ -102,12 +102,14 @@ int b2h_conv_forward(const void* x, int x_dtype, const float* params, const void
 /* ---- K2 fused forward + loss + backward --------------------------------------------------------
  * One iteration of steps/traintest.py:94-120 up to loss.backward():  forward, mask_output,
  * maskedPoseL1 / poderatedPoseL1, and every parameter gradient (conv dgrad/wgrad/bias-grad, ReLU
- * mask).  grads_out: flat fp32 (b2h_param_count), overwritten.  loss_out: 1 float.
- * pred_out nullable (B,T,42) masked prediction.  conf (B,T,21) only for B2H_LOSS_CONFL1. */
+ * mask).  grads_out: flat fp32 (b2h_param_count), overwritten; NULL = run only the fused kernel and
+ * leave the per-CTA partials in the workspace (per-kernel timing).  loss_out: 1 float.
+ * pred_out nullable (B,T,42) masked prediction.  conf (B,T,21) only for B2H_LOSS_CONFL1.
+ * step_dev nullable: device int64 step counter, incremented here (see b2h_adam_step / b2h_train_step). */
 int b2h_train_forward_backward(const void* x, int x_dtype, const float* target, const float* conf,
                                const int32_t* lengths, const float* params, const void* packed,
                                float* grads_out, float* loss_out, float* pred_out, int B, int T, int n_in, int C,
-                               int pos_emb, int loss_kind, int precision, void* workspace,
+                               int pos_emb, int loss_kind, int precision, int64_t* step_dev, void* workspace,
                                int64_t workspace_bytes, void* stream);
 
 /* Backward of ConvModel.forward alone for the modular autograd path (what loss.backward() does
@@ -131,18 +133,21 @@ int b2h_pose_l1(const float* pred, const float* target, const float* scores, con
  * torch.optim.Adam.step with torch defaults (steps/traintest.py:48,121) over the flat buffer:
  * g = grads*grad_scale (grad_scale = 1/world for data parallel); m,v,p updated in place; when
  * `packed` is non-null the new weights are also scattered into the packed operand layouts so the
- * next forward needs no re-pack.  step is 1-based. */
+ * next forward needs no re-pack.  step is 1-based; step_dev (nullable) is a device int64 read
+ * instead of `step` (CUDA-graph replay: the counter is advanced by the train kernel). */
 int b2h_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
-                  double beta1, double beta2, double eps, int64_t step, float grad_scale, void* packed,
-                  int n_in, int C, int pos_emb, void* stream);
+                  double beta1, double beta2, double eps, int64_t step, const int64_t* step_dev, float grad_scale,
+                  void* packed, int n_in, int C, int pos_emb, void* stream);
 
 /* Fast path = b2h_train_forward_backward + b2h_adam_step with the cross-CTA gradient reduction
- * fused into the Adam kernel (2 launches per step, zero host work). */
+ * fused into the Adam kernel (2 launches per step, zero host work).  step_dev (nullable): a device
+ * int64 holding the number of steps taken so far; when given it is incremented on the device and
+ * used instead of `step`, so a captured CUDA graph of this call can be replayed step after step. */
 int b2h_train_step(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,
                    float* params, void* packed, float* exp_avg, float* exp_avg_sq, float* loss_out, int B, int T,
                    int n_in, int C, int pos_emb, int loss_kind, int precision, double lr, double beta1,
-                   double beta2, double eps, int64_t step, void* workspace, int64_t workspace_bytes,
-                   void* stream);
+                   double beta2, double eps, int64_t step, int64_t* step_dev, void* workspace,
+                   int64_t workspace_bytes, void* stream);
 
 /* tcgen05 / TMEM / descriptor self-test (tests/test_tc_probe.py): D = A·B^T for one 128xNx(16*ksteps)
  * bf16 tile staged in the no-swizzle K-major layout the conv kernels use, A rows shifted by `shift`

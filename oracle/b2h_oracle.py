@@ -46,7 +46,7 @@ def format_keypoints(flat, n_dim=2):
     """[x1,y1,c1,x2,...] -> [[x1,y1,c1],...]   text_pose_dataset.py:16-26"""
     n = n_dim + 1
     flat = np.asarray(flat)
-    return flat[: (flat.shape[-1] // n) * n].reshape(flat.shape[:-1] + (-1, n))
+    return flat[..., : (flat.shape[-1] // n) * n].reshape(flat.shape[:-1] + (-1, n))
 
 
 def load_keypoints_arrays(pose75, lhand63, rhand63):
@@ -351,6 +351,27 @@ def adam_reference_step(p, g, m, v, step, lr=2e-4, b1=0.9, b2=0.999, eps=1e-8):
     denom = np.sqrt(v) / math.sqrt(bc2) + eps
     p = p - (lr / bc1) * m / denom
     return p, m, v
+
+
+def adam_conditioned(grads_per_step, weights, lr, eps=1e-8, margin=3.0):
+    """Adam parity is ill-conditioned where a gradient element is close to rounding noise: the update
+    is u = lr*g/(|g|+eps), so du/dg = lr*eps/(|g|+eps)^2 explodes for |g| -> eps (1e-8); an element
+    whose gradient is a near-cancelling sign-sum (the L1 loss produces them) moves by anything in
+    [-lr, lr] depending on summation order, and the reference itself is not reproducible there across
+    thread counts.  With a gradient tolerance of tol*max|g| and a weight tolerance of tol*max|w| the
+    update is within tolerance iff (|g|+eps)^2 >= lr*eps*max|g|/max|w|.  Returns, per parameter name,
+    the mask of elements meeting that bound (times `margin`) at EVERY step (an exact 0 can be an exact
+    cancellation in one summation order and 1e-10 in another, so zeros are excluded too); post-step weight parity is asserted on those, and every element is still
+    bounded by 2*lr per step."""
+    masks = {}
+    for grads in grads_per_step:
+        for k, g in grads.items():
+            g = np.abs(np.asarray(g, dtype=np.float64))
+            wmax = max(float(np.abs(np.asarray(weights[k], dtype=np.float64)).max()), 1e-30)
+            thr = margin * math.sqrt(lr * eps * max(float(g.max()), 1e-30) / wmax)
+            m = g >= thr
+            masks[k] = m if k not in masks else (masks[k] & m)
+    return masks
 
 
 def l1_to_pixels(loss, num_joints=21, upsample=1280):

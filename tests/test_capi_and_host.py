@@ -1,0 +1,125 @@
+"""CPU tier: the C-ABI library loads and exports every symbol include/b2h.h declares; geometry queries;
+host-side logic of the drop-in modules (no compute call happens without a GPU)."""
+import ctypes
+import os
+import pickle
+import random
+import re
+
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+
+import b2h_oracle as oracle
+import hand_pose_sl_b200 as b2h
+from hand_pose_sl_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "b2h.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2h_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/b2h.h but not exported"
+    assert sorted(_lib.exported_symbols()) == syms       # the ctypes table binds exactly the header
+
+
+def test_geometry_queries():
+    assert _lib.param_count(24, 30, 0) == 19032
+    assert _lib.param_count(24, 256, 0) == 740650
+    assert _lib.param_count(24, 30, 1) == 19032 + 30 * 5
+    off = [_lib.param_offset(24, 30, 0, l, b) for l in (1, 2, 3, 4) for b in (0, 1)]
+    sizes = [30 * 24 * 5, 30, 30 * 30 * 5, 30, 30 * 30 * 5, 30, 42 * 30 * 5, 42]
+    assert off == list(np.cumsum([0] + sizes[:-1]))
+    assert _lib.packed_bytes(24, 30, 0) > 0 and _lib.packed_bytes(24, 30, 0) % 128 == 0
+    lib = _lib.load()
+    assert lib.b2h_param_count(24, 100000, 0) < 0 and "unsupported geometry" in _lib.last_error()
+    assert lib.b2h_supported(64, 24, 30, 0, _lib.FP32) == 1
+    assert lib.b2h_supported(64, 24, 30, 0, _lib.BF16) == 1
+    assert lib.b2h_supported(100000, 24, 30, 0, _lib.FP32) == 0
+
+
+def test_null_and_bad_arguments_return_error_codes():
+    lib = _lib.load()
+    assert lib.b2h_conv_forward(None, 0, None, None, None, None, 1, 64, 24, 30, 0, 0, 0, 1.0, None) == -1
+    assert "null pointer" in _lib.last_error()
+    assert lib.b2h_preprocess(None, None, None, 0, None, 0, 64, 0, 1280.0, 1, 1, None, None, None, None, None, None, None,
+                              None, None) == -1
+    assert lib.b2h_pack_weights(None, None, 24, 30, 0, None) == -1
+    assert lib.b2h_adam_step(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 1, None, 1.0, None, 0, 0, 0, None) == -1
+
+
+def test_convmodel_is_a_drop_in_on_the_host_side():
+    torch.manual_seed(0)
+    m = b2h.ConvModel(30, "ReLU", False)
+    sd = oracle.init_params(30, False, seed=0)           # == reference ConvModel under the same seed
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    for k, v in m.state_dict().items():
+        assert v.dtype == torch.float32 and torch.equal(v, sd[k])
+    assert sum(p.numel() for p in m.parameters()) == 19032
+    with pytest.raises(ValueError):
+        b2h.ConvModel(30, "Tanh", False)                 # HandPoseModels.py:37
+    # parameters are views of one flat buffer, and stay so through load_state_dict / deepcopy / pickle
+    assert m._is_flat()
+    g = {k: torch.randn_like(v) for k, v in sd.items()}
+    m.load_state_dict(g)
+    assert m._is_flat() and torch.equal(m.flat_parameters()[:30 * 24 * 5].view(30, 24, 5), g["conv1.weight"])
+    m2 = pickle.loads(pickle.dumps(m))
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    m3 = b2h.ConvModel(30, "ReLU", True)
+    assert m3.conv1.weight.shape == (30, 25, 5) and m3.pos_emb is not None
+    # no CPU fallback: a CPU input is refused loudly
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 64, 12, 2))
+
+
+def test_state_dict_interchanges_with_reference_layout(tmp_path):
+    sd = oracle.init_params(30, False, seed=3)
+    path = tmp_path / "last_model.pth"
+    torch.save(sd, path)                                  # what the reference writes (traintest.py:146)
+    m = b2h.ConvModel(30, "ReLU", False)
+    m.load_state_dict(torch.load(path))
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd[k])
+
+
+def test_fused_adam_state_dict_layout():
+    m = b2h.ConvModel(30, "ReLU", False)
+    opt = b2h.FusedAdam(m.parameters(), lr=2e-4)
+    ref = torch.optim.Adam(m.parameters(), lr=2e-4)
+    a, b = opt.state_dict(), ref.state_dict()
+    assert a["param_groups"][0]["params"] == b["param_groups"][0]["params"]
+    for k in ("lr", "betas", "eps", "weight_decay", "amsgrad"):
+        assert a["param_groups"][0][k] == b["param_groups"][0][k]
+
+
+@settings(max_examples=200, deadline=None)
+@given(n_total=st.integers(1, 5000), n=st.integers(1, 300), sel=st.sampled_from(["first", "randomcrop"]),
+       seed=st.integers(0, 2**31 - 1))
+def test_select_window_matches_oracle(n_total, n, sel, seed):
+    rng = random.Random(seed)
+    state = rng.getstate()
+    s, e = b2h.select_window(n_total, n, sel, rng)
+    rng.setstate(state)
+    draw = rng.randint(0, n_total - n) if (n_total > n and sel == "randomcrop") else None
+    assert (s, e) == oracle.select_window(n_total, n, sel, draw)
+    assert 0 <= s <= e <= n_total and e - s == min(n, n_total)
+
+
+def test_select_window_requires_mode_for_long_clips():
+    with pytest.raises(ValueError):
+        b2h.select_window(100, 10, None)
+
+
+def test_sliding_window_starts():
+    assert list(b2h.sliding_window_starts(200, 64, 64)) == [0, 64, 128, 192]
+    assert list(b2h.sliding_window_starts(65, 64, 16)) == [0, 16, 32, 48, 64]

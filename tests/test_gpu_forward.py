@@ -1,0 +1,107 @@
+"""GPU tier: ConvModel forward through the C-ABI vs the oracle and the reference's golden vectors.
+fp32 mode <= 1e-4 relative, bf16 mode <= 2e-2 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+import b2h_oracle as oracle
+import hand_pose_sl_b200 as b2h
+from conftest import golden_sd, load_golden
+from hand_pose_sl_b200 import _lib, synthetic
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+DEV = "cuda:0"
+
+
+def _model(sd, C, pe, prec):
+    m = b2h.ConvModel(C, "ReLU", pe, precision=prec)
+    m.load_state_dict(sd)
+    return m.to(DEV)
+
+
+def _tc_clean():
+    torch.cuda.synchronize()
+    assert _lib.load().b2h_tc_status() == 0, "tensor-core kernel hit a wait timeout"
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["convmodel_c30_b1.npz", "convmodel_c30.npz", "convmodel_c30_posemb.npz",
+                                  "convmodel_c64.npz", "convmodel_c30_t200.npz"])
+def test_forward_golden(name, prec):
+    g = load_golden(name)
+    m = _model(golden_sd(g), int(g["C"]), bool(g["pos_emb"]), prec)
+    x = torch.from_numpy(g["input_kp"]).to(DEV)
+    with torch.no_grad():
+        y = m(x)
+    _tc_clean()
+    assert y.shape == g["pred"].shape and y.dtype == torch.float32
+    assert oracle.rel_err(y.cpu().numpy(), g["pred"]) <= TOL[prec]
+    # fused mask_output epilogue == reference mask_output on the reference prediction
+    ym = m.predict(x, lengths=torch.from_numpy(g["lengths"]))
+    _tc_clean()
+    assert oracle.rel_err(ym.cpu().numpy(), g["pred_masked"]) <= TOL[prec]
+    for i, ln in enumerate(g["lengths"]):
+        assert not ym[i, int(ln):].any()                 # exact zeros (index work: bit-exact)
+    # fused de-normalise (traintest.py:270-271)
+    yd = m.predict(x, denormalize=1280)
+    assert torch.equal(yd, y * 1280)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,T,C", [(1, 64, 30), (7, 64, 30), (5, 1, 30), (3, 5, 30), (2, 130, 30), (9, 33, 16), (2, 64, 64),
+                                   (300, 64, 30)])
+def test_forward_vs_oracle_shapes(B, T, C, prec):
+    sd = oracle.init_params(C, False, seed=B + T)
+    batch = synthetic.model_batch(B, T, seed=B * 1000 + T)
+    m = _model(sd, C, False, prec)
+    with torch.no_grad():
+        y = m(batch["input_kp"].to(DEV))
+    _tc_clean()
+    ref = oracle.conv_model_forward(sd, batch["input_kp"]).contiguous().numpy()
+    assert oracle.rel_err(y.cpu().numpy(), ref) <= TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_bf16_input_tensor(prec):
+    sd = oracle.init_params(30, False, seed=0)
+    batch = synthetic.model_batch(8, 64, seed=5)
+    m = _model(sd, 30, False, prec)
+    xb = batch["input_kp"].to(DEV).to(torch.bfloat16)
+    with torch.no_grad():
+        y = m(xb)
+    _tc_clean()
+    ref = oracle.conv_model_forward(sd, xb.float().cpu()).contiguous().numpy()
+    assert oracle.rel_err(y.cpu().numpy(), ref) <= TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_config2_full_size_properties(prec):
+    """BASELINE config 2 (B=512 x 64): window independence (any sub-batch gives the same rows), determinism,
+    and a seeded sample of windows against the oracle."""
+    sd = oracle.init_params(30, False, seed=0)
+    batch = synthetic.model_batch(512, 64, seed=1234)
+    m = _model(sd, 30, False, prec)
+    x = batch["input_kp"].to(DEV)
+    with torch.no_grad():
+        y = m(x)
+        y2 = m(x)
+        part = m(x[100:229])
+        perm = torch.randperm(512, generator=torch.Generator().manual_seed(0)).to(DEV)
+        yp = m(x[perm])
+    _tc_clean()
+    assert torch.equal(y, y2)
+    assert torch.equal(part, y[100:229])
+    assert torch.equal(yp, y[perm])
+    pick = [0, 1, 63, 64, 255, 256, 300, 510, 511]
+    ref = oracle.conv_model_forward(sd, batch["input_kp"][pick]).contiguous().numpy()
+    assert oracle.rel_err(y[pick].cpu().numpy(), ref) <= TOL[prec]
+
+
+def test_errors_mirror_reference():
+    m = b2h.ConvModel(30, "ReLU", False).to(DEV)
+    with pytest.raises(RuntimeError):                       # 8 keypoints -> 16 != 24 channels
+        m(torch.zeros(1, 64, 8, 2, device=DEV))
+    mp = b2h.ConvModel(30, "ReLU", True).to(DEV)
+    with pytest.raises(RuntimeError):                       # pos_emb only works for T == 100 (HandPoseModels.py:82)
+        mp(torch.zeros(1, 64, 12, 2, device=DEV))

@@ -1,0 +1,188 @@
+"""GPU tier: loss, gradients, Adam and the fused train step through the C-ABI vs the oracle / golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+import b2h_oracle as oracle
+import hand_pose_sl_b200 as b2h
+from conftest import golden_sd, load_golden
+from hand_pose_sl_b200 import _lib, synthetic
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp32": 1e-4, "bf16": 2e-2}
+DEV = "cuda:0"
+NAMES = ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "conv3.weight", "conv3.bias", "conv4.weight", "conv4.bias"]
+
+
+def _model(sd, C, pe, prec):
+    m = b2h.ConvModel(C, "ReLU", pe, precision=prec)
+    m.load_state_dict(sd)
+    return m.to(DEV)
+
+
+def _batch(g):
+    return {"input_kp": torch.from_numpy(g["input_kp"]).to(DEV), "target_kp": torch.from_numpy(g["target_kp"]).to(DEV),
+            "target_conf": torch.from_numpy(g["target_conf"]).to(DEV), "n_frames": torch.from_numpy(g["lengths"])}
+
+
+def _split(model, flat):
+    out, off = {}, 0
+    for k, p in zip(NAMES, model._ordered_params()):
+        out[k] = flat[off:off + p.numel()].view(p.shape).cpu().numpy()
+        off += p.numel()
+    return out
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("kind", ["L1", "confL1"])
+@pytest.mark.parametrize("name", ["convmodel_c30.npz", "convmodel_c30_b1.npz", "convmodel_c30_posemb.npz", "convmodel_c64.npz",
+                                  "convmodel_c30_t200.npz"])
+def test_loss_and_gradients_golden(name, kind, prec):
+    g = load_golden(name)
+    m = _model(golden_sd(g), int(g["C"]), bool(g["pos_emb"]), prec)
+    loss, grads, pred = b2h.forward_backward(m, _batch(g), loss=kind, want_pred=True)
+    torch.cuda.synchronize()
+    assert abs(float(loss) - g[f"loss_{kind}"][0]) <= TOL[prec] * abs(g[f"loss_{kind}"][0])
+    assert oracle.rel_err(pred.cpu().numpy(), g["pred_masked"]) <= TOL[prec]
+    for k, v in _split(m, grads).items():
+        assert oracle.rel_err(v, g[f"grad_{kind}_" + k.replace(".", "_")]) <= TOL[prec], k
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("kind", ["L1", "confL1"])
+@pytest.mark.parametrize("name", ["convmodel_c30.npz", "convmodel_c64.npz"])
+def test_fused_train_steps_golden(name, kind, prec):
+    """k fused steps (fwd+mask+loss+bwd | reduce+Adam+repack) == k reference steps (traintest.py:94-121)."""
+    g = load_golden(name)
+    sd = golden_sd(g)
+    m = _model(sd, int(g["C"]), bool(g["pos_emb"]), prec)
+    opt = b2h.FusedAdam(m.parameters(), lr=float(g["lr"]))
+    batch = _batch(g)
+    steps = len(g[f"loss_{kind}"])
+    # oracle trajectory for the conditioning mask (see oracle.adam_conditioned)
+    st = oracle.TrainState(sd, lr=float(g["lr"]), pos_emb=bool(g["pos_emb"]))
+    all_grads = []
+    for s in range(steps):
+        loss = b2h.fused_train_step(m, batch, opt, loss=kind)
+        assert abs(float(loss) - g[f"loss_{kind}"][s]) <= TOL[prec] * abs(g[f"loss_{kind}"][s]), s
+        _, gr = oracle.train_step(st, torch.from_numpy(g["input_kp"]), torch.from_numpy(g["target_kp"]),
+                                  torch.from_numpy(g["lengths"]), kind, torch.from_numpy(g["target_conf"]))
+        all_grads.append({k: v.numpy() for k, v in gr.items()})
+    masks = oracle.adam_conditioned(all_grads, sd, float(g["lr"]))
+    for k, v in m.state_dict().items():
+        want = g[f"w{steps}_{kind}_" + k.replace(".", "_")]
+        d = np.abs(v.cpu().numpy() - want)
+        assert d[masks[k]].max() <= TOL[prec] * np.abs(want).max(), k
+        assert d.max() <= 2 * float(g["lr"]) * steps, k
+    # the re-packed operand layouts the Adam kernel wrote == a fresh pack of the new weights
+    packed_by_adam = m._packed.clone()
+    m.mark_packed_stale()
+    assert torch.equal(m.packed_weights(), packed_by_adam)
+    # optimiser state in torch layout
+    osd = opt.state_dict()
+    assert set(osd["state"][0].keys()) >= {"step", "exp_avg", "exp_avg_sq"} and float(osd["state"][0]["step"]) == steps
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_modular_autograd_path_matches_reference_loop(prec):
+    """The reference's own call sequence, unchanged: model(x) -> mask_output -> criterion -> zero_grad ->
+    backward -> optimizer.step (traintest.py:94-121), with the drop-in classes."""
+    g = load_golden("convmodel_c30.npz")
+    sd = golden_sd(g)
+    m = _model(sd, 30, False, prec)
+    opt = b2h.FusedAdam(m.parameters(), lr=float(g["lr"]))
+    crit = b2h.maskedPoseL1()
+    batch = _batch(g)
+    for s in range(3):
+        pred = m(batch["input_kp"])
+        pred = b2h.mask_output(pred, batch["n_frames"])
+        loss = crit(pred, batch["target_kp"], batch["n_frames"])
+        opt.zero_grad()
+        loss.backward()
+        if s == 0:
+            for k, p in zip(NAMES, m._ordered_params()):
+                assert oracle.rel_err(p.grad.cpu().numpy(), g["grad_L1_" + k.replace(".", "_")]) <= TOL[prec], k
+        opt.step()
+        assert abs(loss.item() - g["loss_L1"][s]) <= TOL[prec] * abs(g["loss_L1"][s])
+
+
+def test_stock_torch_adam_also_works_and_repacks():
+    g = load_golden("convmodel_c30.npz")
+    m = _model(golden_sd(g), 30, False, "fp32")
+    opt = torch.optim.Adam(m.parameters(), lr=float(g["lr"]))          # the reference's optimiser, verbatim
+    batch = _batch(g)
+    for s in range(3):
+        pred = b2h.mask_output(m(batch["input_kp"]), batch["n_frames"])
+        loss = b2h.maskedPoseL1()(pred, batch["target_kp"], batch["n_frames"])
+        opt.zero_grad(); loss.backward(); opt.step()
+        assert abs(loss.item() - g["loss_L1"][s]) <= 1e-4 * abs(g["loss_L1"][s])
+
+
+@pytest.mark.parametrize("kind", ["L1", "confL1"])
+def test_criteria_standalone(kind):
+    g = load_golden("convmodel_c30.npz")
+    pred = torch.from_numpy(g["pred_masked"]).to(DEV).requires_grad_(True)
+    tgt, conf, ln = torch.from_numpy(g["target_kp"]), torch.from_numpy(g["target_conf"]), torch.from_numpy(g["lengths"])
+    cp = torch.from_numpy(g["pred_masked"]).requires_grad_(True)
+    if kind == "L1":
+        loss = b2h.maskedPoseL1()(pred, tgt.to(DEV), ln)
+        ref = oracle.masked_pose_l1(cp, tgt, ln)
+    else:
+        loss = b2h.poderatedPoseL1()(pred, tgt.to(DEV), ln, conf)       # scores arrive on the CPU (utils.py:439)
+        ref = oracle.poderated_pose_l1(cp, tgt, ln, conf)
+    loss.backward(); ref.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert oracle.rel_err(pred.grad.cpu().numpy(), cp.grad.numpy()) <= 1e-5
+
+
+def test_mask_output_in_place_bit_exact():
+    g = load_golden("convmodel_c30.npz")
+    y = torch.from_numpy(g["pred"]).to(DEV)
+    out = b2h.mask_output(y, torch.from_numpy(g["lengths"]))
+    assert out.data_ptr() == y.data_ptr()                                # in place, returns the same tensor
+    assert np.array_equal(out.cpu().numpy(), g["pred_masked"])
+
+
+def test_fused_adam_vs_torch_adam_many_steps():
+    torch.manual_seed(1)
+    m = b2h.ConvModel(30, "ReLU", False).to(DEV)
+    ref_p = [p.detach().clone().cpu().requires_grad_(True) for p in m._ordered_params()]
+    ref = torch.optim.Adam(ref_p, lr=1e-3)
+    opt = b2h.FusedAdam(m.parameters(), lr=1e-3)
+    gen = torch.Generator().manual_seed(2)
+    for s in range(10):
+        for p, q in zip(m._ordered_params(), ref_p):
+            gr = torch.randn(q.shape, generator=gen)
+            q.grad = gr.clone(); p.grad = gr.to(DEV)
+        opt.step(); ref.step()
+    for p, q in zip(m._ordered_params(), ref_p):
+        assert oracle.rel_err(p.detach().cpu().numpy(), q.detach().numpy()) <= 1e-6
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_config3_full_size_properties(prec):
+    """BASELINE config 3 (B=256 x 64): the batch gradient is the mean of the two half-batch gradients (the same
+    identity data-parallel training relies on), determinism, loss == criterion on the masked
+    forward, and parity on a 16-window subset against the oracle."""
+    sd = oracle.init_params(30, False, seed=0)
+    batch = synthetic.model_batch(256, 64, seed=1234, ragged=True)
+    m = _model(sd, 30, False, prec)
+    db = {k: (v.to(DEV) if k != "n_frames" else v) for k, v in batch.items()}
+    loss, grads = b2h.forward_backward(m, db)
+    loss2, grads2 = b2h.forward_backward(m, db)
+    assert torch.equal(grads, grads2) and torch.equal(loss, loss2)       # deterministic reduction
+    halves = []
+    for lo in (0, 128):
+        hb = {k: v[lo:lo + 128] for k, v in db.items()}
+        halves.append(b2h.forward_backward(m, hb))
+    gmean = (halves[0][1] + halves[1][1]) / 2
+    assert oracle.rel_err(grads.cpu().numpy(), gmean.cpu().numpy()) <= 1e-5
+    assert abs(float(loss) - float((halves[0][0] + halves[1][0]) / 2)) <= 1e-6 * abs(float(loss))
+    assert abs(float(loss) - float(b2h.validate_batch(m, db))) <= TOL[prec] * abs(float(loss))
+    sub = {k: v[:16] for k, v in batch.items()}
+    st = oracle.TrainState(sd)
+    ref_loss, ref_g = oracle.train_step(st, sub["input_kp"], sub["target_kp"], sub["n_frames"])
+    l16, g16 = b2h.forward_backward(m, {k: (v[:16].to(DEV) if k != "n_frames" else v[:16]) for k, v in batch.items()})
+    assert abs(float(l16) - ref_loss) <= TOL[prec] * abs(ref_loss)
+    for k, v in _split(m, g16).items():
+        assert oracle.rel_err(v, ref_g[k].numpy()) <= TOL[prec], k

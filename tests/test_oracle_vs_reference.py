@@ -1,0 +1,44 @@
+"""CPU tier, build container only: the oracle against the live, unmodified reference classes
+(skipped on the GPU box where /root/reference does not exist)."""
+import numpy as np
+import pytest
+import torch
+
+import b2h_oracle as oracle
+import ref_loader
+from hand_pose_sl_b200 import synthetic
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+
+
+@pytest.mark.parametrize("C,B,T,pe", [(30, 3, 64, False), (30, 2, 100, True), (48, 2, 37, False)])
+def test_forward_loss_grads_live(C, B, T, pe):
+    M, U, _ = ref_loader.load()
+    torch.manual_seed(0)
+    net = M.ConvModel(C, "ReLU", pe)
+    sd = oracle.init_params(C, pe, seed=0)
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, sd[k]), k                  # same construction order -> same init
+    batch = synthetic.model_batch(B, T, seed=7, ragged=True, len_seed=11)
+    x, tgt, conf, ln = batch["input_kp"], batch["target_kp"], batch["target_conf"], batch["n_frames"]
+    ref = net(x)
+    mine = oracle.conv_model_forward(sd, x, pe)
+    assert torch.equal(ref, mine)
+    ref_m = U.mask_output(ref.clone(), ln)
+    assert torch.equal(ref_m, oracle.mask_output(mine.clone(), ln))
+    assert float(U.maskedPoseL1()(ref_m, tgt, ln)) == float(oracle.masked_pose_l1(ref_m, tgt, ln))
+    assert float(U.poderatedPoseL1()(ref_m, tgt, ln, conf)) == float(oracle.poderated_pose_l1(ref_m, tgt, ln, conf))
+
+
+def test_transforms_live():
+    _, U, D = ref_loader.load()
+    pose, lh, rh = synthetic.synthetic_clip(40, seed=5)
+    out = oracle.preprocess_windows(pose, lh, rh, np.array([0]), 40)
+    r_kp, r_cf, l_kp, l_cf, b_kp, b_cf = oracle.load_keypoints_arrays(pose.reshape(40, 75), lh.reshape(40, 63), rh.reshape(40, 63))
+    item = {"body_kp": torch.tensor(b_kp), "right_hand_kp": torch.tensor(r_kp), "left_hand_kp": torch.tensor(l_kp),
+            "body_conf": torch.tensor(b_cf), "right_hand_conf": torch.tensor(r_cf), "left_hand_conf": torch.tensor(l_cf)}
+    for t in (U.WristDifference(), U.ChestDifference(), U.NormalizeFixedFactor(1280), U.BuildRightHandItem()):
+        item = t(item)
+    assert np.array_equal(item["input_kp"].numpy(), out["input_kp"][0])
+    assert np.array_equal(item["target_kp"].numpy(), out["target_kp"][0])
+    assert np.array_equal(item["left_hand_kp"].numpy(), out["left_hand_kp"][0])
