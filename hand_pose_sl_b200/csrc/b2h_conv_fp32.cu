@@ -314,16 +314,17 @@ int fp32_train_grid(const Geo& g, int B, int T) {
 
 int launch_fp32(Fp32Args& p, bool train, cudaStream_t stream, int grid_override) {
   const size_t smem = fp32_smem_bytes(p.geo, p.T, train);
-  if (smem > (size_t)227 * 1024) {
+  if (smem > (size_t)226 * 1024) {
     set_error("fp32 path: window of T=%d, C=%d needs %zu B of shared memory (> 227 KB)", p.T, p.geo.C, smem);
     return B2H_ESHAPE;
   }
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[train ? 1 : 0]) {
-    cudaError_t e = train ? cudaFuncSetAttribute(conv_fp32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                          : cudaFuncSetAttribute(conv_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2H_ECUDA; }
-    attr_set[train ? 1 : 0] = true;
+  // opt in to > 48 KB of dynamic shared memory (dynamic + static must stay <= 227 KB)
+  static size_t attr_bytes[2] = {0, 0};
+  if (smem > attr_bytes[train ? 1 : 0]) {
+    cudaError_t e = train ? cudaFuncSetAttribute(conv_fp32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : cudaFuncSetAttribute(conv_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e)); return B2H_ECUDA; }
+    attr_bytes[train ? 1 : 0] = smem;
   }
   int grid;
   if (train) {

@@ -305,15 +305,15 @@ int launch_tc_fwd(TcFwdArgs& p, cudaStream_t stream) {
   }
   size_t smem;
   tc_plan(p.geo, p.B, p.T, p.G, p.NT, p.RBUF, smem);
-  if (smem > (size_t)227 * 1024) {
+  if (smem > (size_t)225 * 1024) {
     set_error("bf16 forward: T=%d C=%d needs %zu B shared memory", p.T, p.geo.C, smem);
     return B2H_ESHAPE;
   }
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return B2H_ECUDA; }
-    attr = true;
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e)); return B2H_ECUDA; }
+    attr_bytes = smem;
   }
   const int grid = (p.B + p.G - 1) / p.G;
   conv_tc_fwd_kernel<<<grid, kTcThreads, smem, stream>>>(p);

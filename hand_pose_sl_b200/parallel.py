@@ -153,6 +153,5 @@ class DataParallelTrainer:
         self.state["step"] = self.host_steps
 
     def finish(self):
-        for p in self.opt.param_groups[0]["params"]:
-            self.opt.state[p]["step"] = torch.tensor(float(self.host_steps))
+        self.state["step_t"].fill_(float(self.host_steps))
         self.model.packed_weights(fresh_from_kernel=True)

@@ -101,8 +101,7 @@ class TrainStepRunner:
 
     def finish(self):
         """Publish the step count to the optimiser's torch-layout state (for state_dict())."""
-        for p in self.opt.param_groups[0]["params"]:
-            self.opt.state[p]["step"] = torch.tensor(float(self.host_steps))
+        self.state["step_t"].fill_(float(self.host_steps))
         self.model.packed_weights(fresh_from_kernel=True)
 
 

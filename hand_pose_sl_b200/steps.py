@@ -175,12 +175,13 @@ class FusedAdam(torch.optim.Optimizer):
                     v[off:off + n].copy_(ps["exp_avg_sq"].reshape(-1))
                     step = int(ps["step"]) if "step" in ps else step
                 off += n
-            st = {"m": m, "v": v, "step": step}
+            step_t = torch.tensor(float(step))      # ONE host tensor shared by the 8 per-parameter states
+            st = {"m": m, "v": v, "step": step, "step_t": step_t}
             self._flat_state[gi] = st
             off = 0
             for p in group["params"]:
                 n = p.numel()
-                self.state[p] = {"step": torch.tensor(float(st["step"])),
+                self.state[p] = {"step": step_t,
                                  "exp_avg": m[off:off + n].view(p.shape),
                                  "exp_avg_sq": v[off:off + n].view(p.shape)}
                 off += n
@@ -217,8 +218,7 @@ class FusedAdam(torch.optim.Optimizer):
                                              None, float(grad_scale), _lib.ptr(packed), n_in, C, pe,
                                              _lib.stream_ptr(flat.device)))
                 model.packed_weights(fresh_from_kernel=True)
-                for p in group["params"]:
-                    self.state[p]["step"] = torch.tensor(float(st["step"]))
+                st["step_t"].fill_(float(st["step"]))
             else:
                 for p in group["params"]:
                     if p.grad is None:
@@ -272,6 +272,7 @@ def fused_train_step(model: ConvModel, batch, optimizer: FusedAdam, loss="L1"):
                                   _lib.PRECISIONS[model.precision], float(group["lr"]), b1, b2, group["eps"], st["step"],
                                   None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
     model.packed_weights(fresh_from_kernel=True)
+    st["step_t"].fill_(float(st["step"]))
     return loss_out
 
 

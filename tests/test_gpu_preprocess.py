@@ -18,7 +18,7 @@ def _run(pose, lh, rh, starts, T, **kw):
     pre = b2h.PreprocessRightHand(**kw)
     out = pre(torch.from_numpy(pose).to(dev), torch.from_numpy(lh).to(dev), torch.from_numpy(rh).to(dev), starts, T)
     torch.cuda.synchronize()
-    return {k: v.cpu().numpy() for k, v in out.items()}
+    return {k: v.cpu().numpy() for k, v in out.items() if v.dtype != torch.bfloat16}
 
 
 @pytest.mark.parametrize("tag,dif", [("dif", True), ("nodif", False)])

@@ -1,0 +1,36 @@
+"""Short profiling target: a few launches of every hot kernel (K0 preprocess, tcgen05 forward, fused train
+step, Adam) at the BASELINE sizes.  Run plain first, then under ncu (see B200_PROFILING.md)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import hand_pose_sl_b200 as b2h
+from hand_pose_sl_b200 import synthetic
+from hand_pose_sl_b200.runner import ForwardRunner, TrainStepRunner
+
+dev = torch.device("cuda:0")
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+F = 108000
+pose, lh, rh = synthetic.synthetic_clip(F, seed=1234)
+tp, tl, tr = (torch.from_numpy(a).to(dev) for a in (pose, lh, rh))
+pre = b2h.PreprocessRightHand()
+starts = torch.zeros(1, dtype=torch.int64, device=dev)
+for _ in range(reps):
+    pre(tp, tl, tr, starts, F)
+torch.manual_seed(0)
+for prec in ("bf16", "fp32"):
+    fm = b2h.ConvModel(30, "ReLU", False, precision=prec).to(dev)
+    fr = ForwardRunner(fm, 512, 64, x_dtype=torch.bfloat16 if prec == "bf16" else torch.float32)
+    fr.x[0].copy_(synthetic.model_batch(512, 64, seed=99)["input_kp"])
+    for _ in range(reps):
+        fr.run(0)
+m = b2h.ConvModel(30, "ReLU", False, precision="fp32").to(dev)
+opt = b2h.FusedAdam(m.parameters(), lr=2e-4)
+r = TrainStepRunner(m, opt, 256, 64)
+r.load(synthetic.model_batch(256, 64, seed=1234), non_blocking=False)
+for _ in range(reps):
+    r.step(0)
+torch.cuda.synchronize()
+print("prof_target done, loss", float(r.loss[0]))
