@@ -36,9 +36,13 @@ static bool geo_ok(int n_in, int C, int pos_emb, const char* who) {
   return true;
 }
 
+static bool use_tc_train(const Geo& g, int T, int precision) { return precision == B2H_BF16 && tc_tile_ok(g, T, true); }
+
 static int train_nparts(const Geo& g, int B, int T, int precision) {
-  (void)precision;
-  return fp32_train_grid(g, B, T);
+  return use_tc_train(g, T, precision) ? tc_train_grid(g, B, T) : fp32_train_grid(g, B, T);
+}
+static int64_t train_part_stride(const Geo& g, int T, int precision) {
+  return use_tc_train(g, T, precision) ? gp_total(g) : g.P;
 }
 
 }  // namespace b2h
@@ -82,7 +86,7 @@ extern "C" int64_t b2h_workspace_bytes(int B, int T, int n_in, int C, int pos_em
   if (B < 1 || T < 1) return 256;
   Geo g = make_geo(n_in, C, pos_emb);
   const int np = train_nparts(g, B, T, precision);
-  return ((int64_t)np * g.P + np) * 4 + 256;
+  return ((int64_t)np * train_part_stride(g, T, precision) + np) * 4 + 256;
 }
 
 extern "C" int b2h_pack_weights(const float* params, void* packed, int n_in, int C, int pos_emb, void* stream) {
@@ -111,7 +115,10 @@ extern "C" int b2h_conv_forward(const void* x, int x_dtype, const float* params,
     a.y = y; a.B = B; a.T = T; a.apply_mask = apply_mask; a.mode = 0; a.out_scale = out_scale; a.geo = g;
     return launch_fp32(a, false, (cudaStream_t)stream, 0);
   } else if (precision == B2H_BF16) {
-    TcFwdArgs a{};
+    if (tc_tile_ok(g, T, false))   // independent 128-row tiles (T <= 126): persistent tile kernel
+      return launch_tc_tile_fwd(x, x_dtype, params, reinterpret_cast<const char*>(packed), lengths, y, B, T, apply_mask, out_scale, g,
+                                (cudaStream_t)stream);
+    TcFwdArgs a{};                 // long windows: layer-major row-space kernel
     a.x = x; a.x_dtype = x_dtype; a.params = params; a.packed = reinterpret_cast<const char*>(packed); a.lengths = lengths;
     a.y = y; a.B = B; a.T = T; a.apply_mask = apply_mask; a.out_scale = out_scale; a.geo = g;
     return launch_tc_fwd(a, (cudaStream_t)stream);
@@ -137,17 +144,19 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
   } else if (!d_y) { set_error("%s: null d_y", who); return B2H_EINVAL; }
   g = make_geo(n_in, C, pos_emb);
   nparts = train_nparts(g, B, T, precision);
-  const int64_t need = ((int64_t)nparts * g.P + nparts) * 4;
+  const int64_t stride = train_part_stride(g, T, precision);
+  const int64_t need = ((int64_t)nparts * stride + nparts) * 4;
   if (workspace_bytes < need) { set_error("%s: workspace %lld B < %lld B", who, (long long)workspace_bytes, (long long)need); return B2H_EWORKSPACE; }
   partials = reinterpret_cast<float*>(workspace);
-  loss_partials = partials + (size_t)nparts * g.P;
-  // Backward/training currently runs the FFMA kernel for both precisions (fp32 math, fp32 master
-  // weights); the bf16 tensor-core backward replaces it behind the same entry point.
+  loss_partials = partials + (size_t)nparts * stride;
+  // fp32 mode: FFMA kernel.  bf16 mode: tcgen05 tile kernel (T <= 126, C <= 32); other bf16 shapes fall
+  // back to the FFMA kernel -- still CUDA, still fp32 master weights.
   Fp32Args a{};
   a.x = x; a.x_dtype = x_dtype; a.target = target; a.conf = conf; a.d_y = d_y; a.lengths = lengths; a.params = params;
   a.packed = reinterpret_cast<const char*>(packed); a.y = pred_out; a.partials = partials; a.loss_partials = loss_partials;
   a.B = B; a.T = T; a.loss_kind = loss_kind; a.apply_mask = 1; a.mode = mode; a.out_scale = 1.0f; a.geo = g;
   a.step_dev = step_dev;
+  if (use_tc_train(g, T, precision)) return launch_tc_tile_train(a, stream);
   return launch_fp32(a, true, stream, nparts);
 }
 
@@ -162,7 +171,7 @@ extern "C" int b2h_train_forward_backward(const void* x, int x_dtype, const floa
                         loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
                         loss_partials, "b2h_train_forward_backward", reinterpret_cast<long long*>(step_dev));
   if (rc || !grads_out) return rc;   // grads_out == NULL: only the fused kernel runs, partials stay in the workspace
-  return launch_reduce(partials, nparts, g.P, grads_out, loss_partials, loss_out, (cudaStream_t)stream);
+  return launch_reduce(partials, nparts, use_tc_train(g, T, precision) ? 1 : 0, g, grads_out, loss_partials, loss_out, (cudaStream_t)stream);
 }
 
 extern "C" int b2h_conv_backward(const void* x, int x_dtype, const float* d_y, const float* params, const void* packed,
@@ -174,7 +183,7 @@ extern "C" int b2h_conv_backward(const void* x, int x_dtype, const float* d_y, c
                         precision, 2, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
                         loss_partials, "b2h_conv_backward");
   if (rc) return rc;
-  return launch_reduce(partials, nparts, g.P, grads_out, nullptr, nullptr, (cudaStream_t)stream);
+  return launch_reduce(partials, nparts, use_tc_train(g, T, precision) ? 1 : 0, g, grads_out, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int b2h_train_step(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,
@@ -189,7 +198,7 @@ extern "C" int b2h_train_step(const void* x, int x_dtype, const float* target, c
                         loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
                         loss_partials, "b2h_train_step", reinterpret_cast<long long*>(step_dev));
   if (rc) return rc;
-  return launch_adam(params, partials, nparts, exp_avg, exp_avg_sq, g.P, lr, beta1, beta2, eps, step < 1 ? 1 : step,
+  return launch_adam(params, partials, nparts, use_tc_train(g, T, precision) ? 1 : 0, exp_avg, exp_avg_sq, g.P, lr, beta1, beta2, eps, step < 1 ? 1 : step,
                      reinterpret_cast<const long long*>(step_dev), 1.0f, packed, g,
                      loss_partials, loss_out, (cudaStream_t)stream);
 }
@@ -206,7 +215,7 @@ extern "C" int b2h_adam_step(float* params, const float* grads, float* exp_avg, 
     if (g.P != n) { set_error("b2h_adam_step: n=%lld does not match geometry (%d)", (long long)n, g.P); return B2H_ESHAPE; }
   }
   if (n == 0) return B2H_OK;
-  return launch_adam(params, grads, 1, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step < 1 ? 1 : step,
+  return launch_adam(params, grads, 1, 0, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step < 1 ? 1 : step,
                      reinterpret_cast<const long long*>(step_dev), grad_scale, packed, g, nullptr, nullptr, (cudaStream_t)stream);
 }
 

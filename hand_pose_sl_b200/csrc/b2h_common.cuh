@@ -66,6 +66,30 @@ __host__ __device__ inline int64_t umma_b_offset(int k, int kk, int n, int KP, i
   return q * ((int64_t)N * 32) + (int64_t)chunk * (N * 16) + (int64_t)n * 16 + within * 2;
 }
 
+// Gradient-partial layout written by the tensor-core train kernel (coalesced 128-B rows):
+//   per layer l: W part [k][co][kp_l] then bias part [cout_l]
+__host__ __device__ inline int gp_layer_size(const Geo& g, int l) { return B2H_KW * g.cout[l] * g.kp[l] + round_up(g.cout[l], 4); }
+__host__ __device__ inline int gp_layer_off(const Geo& g, int l) {
+  int o = 0;
+  for (int q = 0; q < l; ++q) o += gp_layer_size(g, q);
+  return o;
+}
+__host__ __device__ inline int gp_total(const Geo& g) { return gp_layer_off(g, 4); }
+// flat parameter index -> index in the GP layout
+__host__ __device__ inline int gp_index_of_flat(const Geo& g, int i) {
+  int l = 0;
+  for (int q = 1; q < 4; ++q)
+    if (i >= g.w_off[q]) l = q;
+  const int base = gp_layer_off(g, l);
+  if (i >= g.b_off[l]) return base + B2H_KW * g.cout[l] * g.kp[l] + (i - g.b_off[l]);
+  const int cin = g.cin[l];
+  const int rel = i - g.w_off[l];
+  const int co = rel / (cin * B2H_KW);
+  const int rem = rel - co * cin * B2H_KW;
+  const int ci = rem / B2H_KW, k = rem - ci * B2H_KW;
+  return base + (k * g.cout[l] + co) * g.kp[l] + ci;
+}
+
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 void count_launch(int n = 1);
@@ -101,9 +125,17 @@ bool tc_fwd_supported(const Geo& g, int T);
 int launch_tc_probe(const void* a, const void* b, float* out, int n, int ksteps, int shift, int variant, cudaStream_t stream);
 int tc_status_and_clear();
 
+struct TcTileArgs;
+int tc_train_grid(const Geo& g, int B, int T);
+bool tc_tile_ok(const Geo& g, int T, bool train);
+int launch_tc_tile_fwd(const void* x, int x_dtype, const float* params, const char* packed, const int32_t* lengths, float* y,
+                       int B, int T, int apply_mask, float out_scale, const Geo& g, cudaStream_t stream);
+int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream);
+
 int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t stream);
-int launch_reduce(const float* partials, int nparts, int P, float* grads, const float* loss_partials, float* loss_out, cudaStream_t stream);
-int launch_adam(float* params, const float* grads, int nparts, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+int launch_reduce(const float* partials, int nparts, int gp_layout, const Geo& g, float* grads, const float* loss_partials,
+                  float* loss_out, cudaStream_t stream);
+int launch_adam(float* params, const float* grads, int nparts, int gp_layout, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                 double eps, int64_t step, const long long* step_dev, float grad_scale, void* packed, const Geo& g,
                 const float* loss_partials, float* loss_out, cudaStream_t stream);
 int launch_mask_output(float* y, const int32_t* lengths, int B, int T, int row, cudaStream_t stream);

@@ -349,3 +349,5 @@ int tc_status_and_clear() {
 }
 
 }  // namespace b2h
+
+#include "b2h_train_tc.cuh"

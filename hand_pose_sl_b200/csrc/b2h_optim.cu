@@ -38,12 +38,16 @@ __global__ void pack_kernel(const float* __restrict__ params, char* packed, Geo 
 }
 
 // grads[i] = sum_c partials[c][i];  loss = sum_c loss_partials[c]   (fixed order -> deterministic)
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int nparts, int P, float* __restrict__ grads,
-                                       const float* __restrict__ loss_partials, float* __restrict__ loss_out) {
+__global__ void reduce_partials_kernel(const float* __restrict__ partials, int nparts, int gp_layout, Geo g,
+                                       float* __restrict__ grads, const float* __restrict__ loss_partials,
+                                       float* __restrict__ loss_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P) {
+  if (i < g.P) {
+    // gp_layout: the tensor-core kernel writes [k][co][ci_pad] rows (coalesced); FFMA kernel writes flat order
+    const int src = gp_layout ? gp_index_of_flat(g, i) : i;
+    const size_t stride = gp_layout ? (size_t)gp_total(g) : (size_t)g.P;
     float s = 0.f;
-    for (int c = 0; c < nparts; ++c) s += partials[(size_t)c * P + i];
+    for (int c = 0; c < nparts; ++c) s += partials[(size_t)c * stride + src];
     grads[i] = s;
   }
   if (blockIdx.x == 0 && threadIdx.x < 32 && loss_out) {
@@ -56,7 +60,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
 }
 
 struct AdamArgs {
-  float* params; const float* grads; int nparts; int64_t n;
+  float* params; const float* grads; int nparts; int gp_layout; int64_t n;
   float* m; float* v;
   float beta1, beta2, one_minus_b1, one_minus_b2, step_size, inv_bc2_sqrt, eps, grad_scale;
   double lr_d, beta1_d, beta2_d;
@@ -83,7 +87,9 @@ __global__ void adam_kernel(AdamArgs a) {
   }
   if (i < a.n) {
     float gr = 0.f;
-    for (int c = 0; c < a.nparts; ++c) gr += a.grads[(size_t)c * a.n + i];
+    const int src = a.gp_layout ? gp_index_of_flat(a.g, (int)i) : (int)i;
+    const size_t stride = a.gp_layout ? (size_t)gp_total(a.g) : (size_t)a.n;
+    for (int c = 0; c < a.nparts; ++c) gr += a.grads[(size_t)c * stride + src];
     gr *= a.grad_scale;
     float m = a.m[i], v = a.v[i], p = a.params[i];
     m = fmaf(gr - m, a.one_minus_b1, m);
@@ -168,18 +174,18 @@ int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t st
   return check_launch("pack_kernel");
 }
 
-int launch_reduce(const float* partials, int nparts, int P, float* grads, const float* loss_partials, float* loss_out,
-                  cudaStream_t stream) {
-  reduce_partials_kernel<<<(P + 255) / 256, 256, 0, stream>>>(partials, nparts, P, grads, loss_partials, loss_out);
+int launch_reduce(const float* partials, int nparts, int gp_layout, const Geo& g, float* grads, const float* loss_partials,
+                  float* loss_out, cudaStream_t stream) {
+  reduce_partials_kernel<<<(g.P + 255) / 256, 256, 0, stream>>>(partials, nparts, gp_layout, g, grads, loss_partials, loss_out);
   count_launch();
   return check_launch("reduce_partials_kernel");
 }
 
-int launch_adam(float* params, const float* grads, int nparts, float* m, float* v, int64_t n, double lr, double beta1,
+int launch_adam(float* params, const float* grads, int nparts, int gp_layout, float* m, float* v, int64_t n, double lr, double beta1,
                 double beta2, double eps, int64_t step, const long long* step_dev, float grad_scale, void* packed, const Geo& g,
                 const float* loss_partials, float* loss_out, cudaStream_t stream) {
   AdamArgs a;
-  a.params = params; a.grads = grads; a.nparts = nparts; a.n = n; a.m = m; a.v = v;
+  a.params = params; a.grads = grads; a.nparts = nparts; a.gp_layout = gp_layout; a.n = n; a.m = m; a.v = v;
   a.beta1 = (float)beta1; a.beta2 = (float)beta2;
   a.one_minus_b1 = (float)(1.0 - beta1); a.one_minus_b2 = (float)(1.0 - beta2);
   const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);

@@ -1,0 +1,505 @@
+// bf16 mode, tile kernel: forward (+ masked-L1 loss + full backward) of independent 128-row tiles on
+// tcgen05 / TMEM.  Included by b2h_conv_tc.cu (same translation unit as the PTX layer).
+//
+// Reference semantics (paths relative to the reference root):
+//   ConvModel.forward                 body2hand/src/models/HandPoseModels.py:40-64
+//   mask_output                       body2hand/src/steps/utils.py:309-312
+//   maskedPoseL1 / poderatedPoseL1    body2hand/src/steps/utils.py:413-452
+//   loss.backward()                   body2hand/src/steps/traintest.py:120
+//
+// Tile geometry.  A tile is 128 TMEM lanes of output rows made of `nhalf` independent row segments:
+//   mode B (T <= 64): two segments of 64 rows, one M=64 MMA each (TMEM lanes 32q+i and 32q+16+i), every
+//                     segment holding g = floor(66/(T+2)) whole windows -> T=64: 2 windows per tile, no
+//                     padded-row waste;
+//   mode A (64 < T <= 126): one segment of 128 rows, M=128, one window.
+// A segment lives in shared memory as [2 zero rows][window][2 zero rows][window]...[zero rows] in the
+// no-swizzle K-major canonical layout [channel/8][row][8 ch] (16-B rows), so conv tap k is a +16*k byte
+// shift of the A descriptor and the SAME buffer also serves, read as an MN-major operand, as A (dZ^T) or
+// B (layer input) of the weight-gradient GEMM (reduction over frames).
+//
+// Per tile: F1 F2 F3 F4(+loss,+dY) | D4,W4 | D3,W3 | D2,W2 | W1.   F/D = conv GEMM + epilogue
+// (tcgen05.ld -> bias/ReLU or ReLU-mask -> bf16 -> st.shared); W = weight/bias-gradient GEMMs that keep
+// accumulating in TMEM across all tiles of the CTA (issued right after D so they run under D's epilogue) and
+// are read out once at the end into the CTA's slice of the partials workspace (deterministic 2-stage sum).
+#pragma once
+
+namespace b2h {
+using namespace tc;
+
+struct TcTileArgs {
+  const void* x; int x_dtype;
+  const float* target; const float* conf; const float* d_y; const int32_t* lengths;
+  const float* params; const char* packed;
+  float* y;               // forward output / masked prediction (nullable in train mode)
+  float* partials;        // [grid][GP]  (gradient-partial layout, see gp_* below)
+  float* loss_partials;   // [grid]
+  long long* step_dev;
+  int B, T, loss_kind, apply_mask, mode;   // mode 0 = forward only, 1 = train (loss inside), 2 = backward of given d_y
+  float out_scale;
+  int n_tiles, nhalf, MB, HR, gh;          // tile geometry
+  Geo geo;
+};
+
+constexpr int kTileThreads = 128;
+constexpr int kAccCol = 0;        // forward / dgrad accumulator: columns [0, 64)
+constexpr int kWgCol = 64;        // weight-gradient accumulators: 2 layer pairs x (5 taps x 32 + 8 bias) columns
+constexpr int kWgPairCols = 5 * 32 + 8;
+
+struct TileSmem {   // byte offsets into dynamic smem
+  int g0, g1, x, a1, a2, a3, ones, wf[4], wd[4], total;
+};
+
+__host__ __device__ inline TileSmem tile_smem_layout(const Geo& g, int rows, bool train) {
+  TileSmem s;
+  const int CH = rows * 16;
+  int o = 0;
+  // gradient buffers first: the M=64 MN-major A operand of the weight-gradient GEMM spans 8 chunks from
+  // their start and must stay inside the allocation (the extra chunks only feed ignored accumulator rows)
+  s.g0 = o; o += train ? 6 * CH : 0;
+  s.g1 = o; o += train ? 4 * CH : 0;
+  s.x = o;  o += (g.kp[0] / 8) * CH;
+  s.a1 = o; o += (g.kp[1] / 8) * CH;
+  s.a2 = o; o += (g.kp[1] / 8) * CH;
+  s.a3 = o; o += train ? (g.kp[1] / 8) * CH : 0;
+  s.ones = o; o += train ? CH : 0;
+  for (int l = 0; l < 4; ++l) { s.wf[l] = o; o += B2H_KW * g.kp[l] * g.np_[l] * 2; }
+  for (int l = 0; l < 4; ++l) {
+    s.wd[l] = o;
+    if (train && l > 0) o += B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2;
+  }
+  s.total = o;
+  return s;
+}
+
+__device__ __forceinline__ void store8_bf16(unsigned char* buf, int CH, int row, int chunk, const float* v) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(buf + (size_t)chunk * CH + (size_t)row * 16) = q;
+}
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& q, float* f) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArgs p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float bias_s[4][64];
+  __shared__ float red_s[4];
+  const Geo& g = p.geo;
+  const int T = p.T, MB = p.MB, HR = p.HR, nhalf = p.nhalf, gh = p.gh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rows = nhalf * HR;
+  const int CH = rows * 16;
+  const TileSmem L = tile_smem_layout(g, rows, TRAIN);
+  unsigned char* G0 = smem + L.g0;
+  unsigned char* G1 = smem + L.g1;
+  unsigned char* X = smem + L.x;
+  unsigned char* A1 = smem + L.a1;
+  unsigned char* A2 = smem + L.a2;
+  unsigned char* A3 = smem + L.a3;
+  unsigned char* ONES = smem + L.ones;
+
+  // this thread's row: TMEM lane == tid
+  const int hh = (nhalf == 2) ? ((tid >> 4) & 1) : 0;
+  const int m = (nhalf == 2) ? ((tid >> 5) * 16 + (tid & 15)) : tid;
+  const int row = hh * HR + 2 + m;
+  const int wj = m / (T + 2), t = m - wj * (T + 2);
+  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, TRAIN ? 512 : 64);
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (TRAIN && p.step_dev && blockIdx.x == 0 && tid == 0) *p.step_dev += 1;
+  // weights (packed bf16 UMMA blocks) -> smem, once per CTA
+  for (int l = 0; l < 4; ++l) {
+    const int nb = B2H_KW * g.kp[l] * g.np_[l] * 2;
+    const uint4* src = reinterpret_cast<const uint4*>(p.packed + g.tf_off[l]);
+    uint4* dst = reinterpret_cast<uint4*>(smem + L.wf[l]);
+    for (int i = tid; i < nb / 16; i += kTileThreads) dst[i] = __ldg(src + i);
+    if (TRAIN && l > 0) {
+      const int nd = B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2;
+      const uint4* s2 = reinterpret_cast<const uint4*>(p.packed + g.td_off[l]);
+      uint4* d2 = reinterpret_cast<uint4*>(smem + L.wd[l]);
+      for (int i = tid; i < nd / 16; i += kTileThreads) d2[i] = __ldg(s2 + i);
+    }
+  }
+  for (int i = tid; i < 4 * 64; i += kTileThreads) {
+    const int l = i >> 6, c = i & 63;
+    bias_s[l][c] = (c < g.cout[l]) ? __ldg(p.params + g.b_off[l] + c) : 0.0f;
+  }
+  {  // zero every activation / gradient buffer once: pad rows and pad channels stay zero
+    const int act_bytes = L.wf[0];
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < act_bytes / 16; i += kTileThreads) z[i] = zero;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  uint32_t phase = 0;
+  float loss_acc = 0.0f;
+  bool wg_started = false;
+  const int wpt = nhalf * gh;                      // windows per tile
+  const uint32_t idesc_M = (nhalf == 2) ? 64 : 128;
+
+  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const int wbase = tile * wpt;
+    const int gw = wbase + hh * gh + wj;           // this thread's global window
+    const bool valid = (t < T) && (wj < gh) && (gw < p.B);
+    int len = T;
+    if (valid && p.lengths) { len = p.lengths[gw]; len = len < 0 ? 0 : (len > T ? T : len); }
+
+    // ---- stage inputs: one thread per row, (n_in) channels NWC -> X [chunk][row][8] bf16 ----
+    {
+      const int n_in = g.n_in, pe = g.pos_emb;
+      const int nch0 = g.kp[0] / 8;
+      if (valid && pe == 0 && (n_in & 7) == 0) {
+        const int cpr = n_in >> 3;
+        if (p.x_dtype == B2H_DT_F32) {
+          const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + ((size_t)gw * T + t) * n_in);
+          for (int c8 = 0; c8 < cpr; ++c8) {
+            const float4 lo = __ldg(src + 2 * c8), hi = __ldg(src + 2 * c8 + 1);
+            const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            store8_bf16(X, CH, row, c8, v);
+          }
+        } else {
+          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + ((size_t)gw * T + t) * n_in);
+          for (int c8 = 0; c8 < cpr; ++c8) *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = __ldg(src + c8);
+        }
+      } else if (valid) {
+        for (int c8 = 0; c8 < nch0; ++c8) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int cc = c8 * 8 + e;            // channel in the conv1 input (pos-emb row first)
+            float val = 0.0f;
+            if (pe && cc == 0) val = __fdiv_rn((float)t, 100.0f);                // HandPoseModels.py:70-82
+            else if (cc - pe < n_in && cc - pe >= 0) {
+              const size_t gi = ((size_t)gw * T + t) * n_in + (cc - pe);
+              val = (p.x_dtype == B2H_DT_F32) ? __ldg(reinterpret_cast<const float*>(p.x) + gi)
+                                              : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.x)[gi]);
+            }
+            v[e] = val;
+          }
+          store8_bf16(X, CH, row, c8, v);
+        }
+      } else {
+        const uint4 zero = make_uint4(0, 0, 0, 0);
+        for (int c8 = 0; c8 < nch0; ++c8) *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = zero;
+      }
+      if (TRAIN) {   // ones column (B operand of the bias-gradient GEMM): 1 on real frames
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (valid) o.x = 0x00003F80u;             // bf16(1.0) in element 0
+        *reinterpret_cast<uint4*>(ONES + (size_t)row * 16) = o;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // =========================== forward: 4 conv layers ===========================
+    for (int l = 0; l < 4; ++l) {
+      unsigned char* bin = (l == 0) ? X : (l == 1) ? A1 : (l == 2) ? A2 : (TRAIN ? A3 : A1);
+      unsigned char* bout = (l == 0) ? A1 : (l == 1) ? A2 : (TRAIN ? A3 : A1);
+      const int KS = g.kp[l] >> 4, N = g.np_[l];
+      if (tid == 0) {
+        const uint32_t idesc = make_idesc_bf16(idesc_M, N, 0, 0);
+        const uint32_t a_base = smem_u32(bin), w_base = smem_u32(smem + L.wf[l]);
+        for (int h = 0; h < nhalf; ++h) {
+          uint32_t acc = 0;
+          for (int k = 0; k < B2H_KW; ++k)
+            for (int s = 0; s < KS; ++s) {
+              // output row 2+m of segment h reads input row m+k
+              const uint64_t ad = make_smem_desc(a_base + (2 * s) * CH + (h * HR + k) * 16, CH, 128);
+              const uint64_t bd = make_smem_desc(w_base + (k * KS + s) * (N * 32), N * 16, 128);
+              umma_bf16(tbase + kAccCol + ((uint32_t)(h * 16) << 16), ad, bd, idesc, acc);
+              acc = 1;
+            }
+        }
+        umma_commit(&bar);
+      }
+      __syncwarp();
+      mbar_wait(&bar, phase, 20 + l);
+      phase ^= 1;
+      tc_fence_after();
+      const uint32_t taddr = tbase + lane_addr + kAccCol;
+      if (l < 3) {
+        for (int c0 = 0; c0 < N; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) f[q] = valid ? fmaxf(__uint_as_float(v[q]) + bias_s[l][c0 + q], 0.0f) : 0.0f;
+          store8_bf16(bout, CH, row, c0 >> 3, f);
+          store8_bf16(bout, CH, row, (c0 >> 3) + 1, f + 8);
+        }
+      } else {
+        // layer 4 epilogue: prediction (+ mask_output), and in train mode the criterion and d(loss)/d(pred)
+        float n_el = 0.f, scale = 0.f;
+        const float* tg = nullptr; const float* cf = nullptr; const float* dy = nullptr;
+        if (TRAIN && valid) {
+          n_el = (float)len * (float)B2H_COUT;
+          scale = (p.loss_kind == B2H_LOSS_L1) ? (1.0f / (float)p.B) / n_el : 1.0f / n_el;
+          if (p.mode == 1) {
+            tg = p.target + ((size_t)gw * T + t) * B2H_COUT;
+            cf = p.conf ? p.conf + ((size_t)gw * T + t) * (B2H_COUT / 2) : nullptr;
+          } else {
+            dy = p.d_y + ((size_t)gw * T + t) * B2H_COUT;
+          }
+        }
+        float* yrow = (valid && p.y) ? p.y + ((size_t)gw * T + t) * B2H_COUT : nullptr;
+        float sum = 0.f;
+        for (int c0 = 0; c0 < N; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          float gq[16];
+#pragma unroll
+          for (int q = 0; q < 16; q += 2) {
+            const int c = c0 + q;
+            float ga = 0.f, gb = 0.f;
+            if (valid && c < B2H_COUT) {
+              float a = __uint_as_float(v[q]) + bias_s[3][c];
+              float b = __uint_as_float(v[q + 1]) + bias_s[3][c + 1];
+              const bool masked = (TRAIN || p.apply_mask) && (t >= len);       // mask_output  utils.py:309-312
+              if (masked) { a = 0.0f; b = 0.0f; }
+              else if (!TRAIN && p.out_scale != 1.0f) { a *= p.out_scale; b *= p.out_scale; }
+              if (yrow) *reinterpret_cast<float2*>(yrow + c) = make_float2(a, b);
+              if (TRAIN && !masked) {
+                if (p.mode == 1) {
+                  const float2 tv = __ldg(reinterpret_cast<const float2*>(tg + c));
+                  float da, db, s = 1.0f;
+                  if (p.loss_kind == B2H_LOSS_L1) { da = a - tv.x; db = b - tv.y; }     // utils.py:422-426
+                  else {
+                    s = __ldg(cf + (c >> 1));
+                    da = __fsub_rn(__fmul_rn(a, s), __fmul_rn(tv.x, s));                 // utils.py:447-450
+                    db = __fsub_rn(__fmul_rn(b, s), __fmul_rn(tv.y, s));
+                  }
+                  sum += fabsf(da) + fabsf(db);
+                  ga = (da > 0.f ? 1.f : (da < 0.f ? -1.f : 0.f)) * s * scale;
+                  gb = (db > 0.f ? 1.f : (db < 0.f ? -1.f : 0.f)) * s * scale;
+                } else {
+                  const float2 d2 = __ldg(reinterpret_cast<const float2*>(dy + c));
+                  ga = d2.x; gb = d2.y;
+                }
+              }
+            }
+            gq[q] = ga; gq[q + 1] = gb;
+          }
+          if (TRAIN) {
+            store8_bf16(G0, CH, row, c0 >> 3, gq);
+            store8_bf16(G0, CH, row, (c0 >> 3) + 1, gq + 8);
+          }
+        }
+        if (TRAIN && p.mode == 1) {
+          // per-sample mean = sum_{t<len} |d| / (len*42)  (utils.py:426 / :450): accumulate sum/n_el
+          float contrib = (valid && t < len) ? sum / n_el : 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+          if (lane == 0) red_s[warp] = contrib;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+    }
+    if (TRAIN && p.mode == 1 && tid == 0) loss_acc += red_s[0] + red_s[1] + red_s[2] + red_s[3];
+
+    if (TRAIN) {
+      // =========================== backward ===========================
+      // dZ_l (grad wrt layer l's pre-activation) ping-pongs G0 (l=3) -> G1 (l=2) -> G0 (l=1) -> G1 (l=0)
+      for (int l = 3; l >= 0; --l) {
+        unsigned char* gz = ((3 - l) & 1) ? G1 : G0;          // dZ_l
+        unsigned char* gnext = ((3 - l) & 1) ? G0 : G1;       // dZ_{l-1}
+        unsigned char* ain = (l == 0) ? X : (l == 1) ? A1 : (l == 2) ? A2 : A3;   // layer l's input activation
+        if (tid == 0) {
+          if (l > 0) {  // dgrad: dA_{l-1}[r][ci] = sum_{k',co} dZ_l[r+k'-2][co] * W_l[co][ci][4-k']
+            const int KSd = round_up(g.cout[l], 16) >> 4, Nd = round_up(g.cin[l], 16);
+            const uint32_t idesc = make_idesc_bf16(idesc_M, Nd, 0, 0);
+            const uint32_t a_base = smem_u32(gz), w_base = smem_u32(smem + L.wd[l]);
+            for (int h = 0; h < nhalf; ++h) {
+              uint32_t acc = 0;
+              for (int k = 0; k < B2H_KW; ++k)
+                for (int s = 0; s < KSd; ++s) {
+                  const uint64_t ad = make_smem_desc(a_base + (2 * s) * CH + (h * HR + k) * 16, CH, 128);
+                  const uint64_t bd = make_smem_desc(w_base + (k * KSd + s) * (Nd * 32), Nd * 16, 128);
+                  umma_bf16(tbase + kAccCol + ((uint32_t)(h * 16) << 16), ad, bd, idesc, acc);
+                  acc = 1;
+                }
+            }
+            umma_commit(&bar);
+          }
+          // wgrad: dW_l[k][co][ci] += sum_r dZ_l[r][co] * in_l[r+k-2][ci];  db_l[co] += sum_r dZ_l[r][co]
+          // A = dZ_l read MN-major (M = co, 8 chunks), B = in_l read MN-major (N = ci), K = 16 frames per MMA
+          {
+            const int Nw = g.kp[l];
+            const uint32_t idw = make_idesc_bf16(64, Nw, 1, 1), idb = make_idesc_bf16(64, 8, 1, 1);
+            const uint32_t a_base = smem_u32(gz), b_base = smem_u32(ain), o_base = smem_u32(ONES);
+            const uint32_t dcol = tbase + kWgCol + (l >> 1) * kWgPairCols + ((uint32_t)((l & 1) * 16) << 16);
+            const uint32_t accw = wg_started ? 1u : 0u;
+            for (int h = 0; h < nhalf; ++h)
+              for (int s = 0; s < MB / 16; ++s) {
+                const uint32_t first = (h == 0 && s == 0) ? accw : 1u;
+                const uint32_t r0 = (h * HR + 2 + 16 * s) * 16;
+                const uint64_t ad = make_smem_desc(a_base + r0, 128, CH);
+                for (int k = 0; k < B2H_KW; ++k) {
+                  const uint64_t bd = make_smem_desc(b_base + r0 + (k - 2) * 16, 128, CH);
+                  umma_bf16(dcol + k * 32, ad, bd, idw, first);
+                }
+                const uint64_t od = make_smem_desc(o_base + r0, 128, CH);
+                umma_bf16(dcol + 5 * 32, ad, od, idb, first);
+              }
+            if (l == 0) umma_commit(&bar);     // last MMAs of the tile: fence the buffers before restaging
+          }
+        }
+        __syncwarp();
+        mbar_wait(&bar, phase, 30 + l);
+        phase ^= 1;
+        tc_fence_after();
+        if (l > 0) {
+          // dZ_{l-1} = dA_{l-1} * (a_{l-1} > 0)     (ReLU backward on the saved activation)
+          const int Nd = round_up(g.cin[l], 16);
+          const uint32_t taddr = tbase + lane_addr + kAccCol;
+          for (int c0 = 0; c0 < Nd; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);
+            tmem_ld_wait();
+            float f[16], act[16];
+            bf16x8_to_float(*reinterpret_cast<const uint4*>(ain + (size_t)(c0 >> 3) * CH + (size_t)row * 16), act);
+            bf16x8_to_float(*reinterpret_cast<const uint4*>(ain + (size_t)((c0 >> 3) + 1) * CH + (size_t)row * 16), act + 8);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) f[q] = (valid && act[q] > 0.0f) ? __uint_as_float(v[q]) : 0.0f;
+            store8_bf16(gnext, CH, row, c0 >> 3, f);
+            store8_bf16(gnext, CH, row, (c0 >> 3) + 1, f + 8);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+      }
+      wg_started = true;
+    }
+  }
+
+  if (TRAIN) {
+    // ---- read the weight / bias gradient accumulators out into this CTA's partial slice ----
+    float* part = p.partials + (size_t)blockIdx.x * gp_total(g);
+    if (!wg_started) {   // CTA had no tile (grid > n_tiles never happens, but keep the slice defined)
+      for (int i = tid; i < gp_total(g); i += kTileThreads) part[i] = 0.0f;
+    } else {
+      for (int l = 0; l < 4; ++l) {
+        // layer l's accumulators sit in TMEM lanes 32q + 16*(l&1) + i  <->  co = 16q + i
+        const int co = warp * 16 + (lane & 15);
+        const bool mine = ((lane >> 4) == (l & 1)) && co < g.cout[l];
+        const int Nw = g.kp[l];
+        float* lp = part + gp_layer_off(g, l);
+        const uint32_t dcol = tbase + lane_addr + kWgCol + (l >> 1) * kWgPairCols;
+        for (int k = 0; k < B2H_KW; ++k)
+          for (int c0 = 0; c0 < Nw; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(dcol + k * 32 + c0, v);
+            tmem_ld_wait();
+            if (mine) {
+              float4* dst = reinterpret_cast<float4*>(lp + ((size_t)k * g.cout[l] + co) * Nw + c0);
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                     __uint_as_float(v[4 * q + 3]));
+            }
+          }
+        {
+          uint32_t v[16];
+          tmem_ld16(dcol + 5 * 32, v);     // 8 valid columns; column 0 holds db (ones sits in element 0)
+          tmem_ld_wait();
+          if (mine) lp[B2H_KW * g.cout[l] * Nw + co] = __uint_as_float(v[0]);
+        }
+      }
+    }
+    if (tid == 0 && p.loss_partials)
+      p.loss_partials[blockIdx.x] = (p.loss_kind == B2H_LOSS_L1) ? loss_acc / (float)p.B : loss_acc;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, TRAIN ? 512 : 64);
+}
+
+// ---- host side ----
+inline bool tc_tile_supported(const Geo& g, int T, bool train) {
+  if (T < 1 || T > 126) return false;
+  if (g.kp[0] > 32 || g.kp[1] > 32) return !train && g.kp[0] <= 64 && g.kp[1] <= 64;
+  return true;
+}
+
+inline void tc_tile_plan(const Geo& g, int B, int T, bool train, TcTileArgs& p, size_t& smem, int& grid) {
+  if (T <= 64) { p.nhalf = 2; p.MB = 64; }
+  else { p.nhalf = 1; p.MB = 128; }
+  p.HR = p.MB + 8;
+  p.gh = (p.MB + 2) / (T + 2);
+  const int wpt = p.nhalf * p.gh;
+  p.n_tiles = (B + wpt - 1) / wpt;
+  smem = (size_t)tile_smem_layout(g, p.nhalf * p.HR, train).total;
+  int per_sm = train ? 1 : (int)((size_t)220 * 1024 / (smem + 2048));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  grid = num_sms() * per_sm;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+}
+
+int tc_train_grid(const Geo& g, int B, int T) {
+  TcTileArgs p{};
+  size_t smem; int grid;
+  tc_tile_plan(g, B, T, true, p, smem, grid);
+  return grid;
+}
+
+int launch_tc_tile(TcTileArgs& p, bool train, cudaStream_t stream) {
+  size_t smem; int grid;
+  tc_tile_plan(p.geo, p.B, p.T, train, p, smem, grid);
+  if (smem > (size_t)225 * 1024) { set_error("tensor-core tile kernel: %zu B shared memory needed", smem); return B2H_ESHAPE; }
+  static size_t attr_bytes[2] = {0, 0};
+  if (smem > attr_bytes[train ? 1 : 0]) {
+    cudaError_t e = train ? cudaFuncSetAttribute(conv_tc_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                          : cudaFuncSetAttribute(conv_tc_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e)); return B2H_ECUDA; }
+    attr_bytes[train ? 1 : 0] = smem;
+  }
+  if (train) conv_tc_tile_kernel<true><<<grid, kTileThreads, smem, stream>>>(p);
+  else conv_tc_tile_kernel<false><<<grid, kTileThreads, smem, stream>>>(p);
+  count_launch();
+  return check_launch(train ? "conv_tc_tile_kernel<train>" : "conv_tc_tile_kernel<fwd>");
+}
+
+
+bool tc_tile_ok(const Geo& g, int T, bool train) { return tc_tile_supported(g, T, train); }
+
+int launch_tc_tile_fwd(const void* x, int x_dtype, const float* params, const char* packed, const int32_t* lengths, float* y,
+                       int B, int T, int apply_mask, float out_scale, const Geo& g, cudaStream_t stream) {
+  TcTileArgs p{};
+  p.x = x; p.x_dtype = x_dtype; p.params = params; p.packed = packed; p.lengths = lengths; p.y = y;
+  p.B = B; p.T = T; p.apply_mask = apply_mask; p.mode = 0; p.out_scale = out_scale; p.geo = g;
+  return launch_tc_tile(p, false, stream);
+}
+
+int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream) {
+  TcTileArgs p{};
+  p.x = a.x; p.x_dtype = a.x_dtype; p.target = a.target; p.conf = a.conf; p.d_y = a.d_y; p.lengths = a.lengths;
+  p.params = a.params; p.packed = a.packed; p.y = a.y; p.partials = a.partials; p.loss_partials = a.loss_partials;
+  p.step_dev = a.step_dev; p.B = a.B; p.T = a.T; p.loss_kind = a.loss_kind; p.apply_mask = 1; p.mode = a.mode;
+  p.out_scale = 1.0f; p.geo = a.geo;
+  return launch_tc_tile(p, true, stream);
+}
+
+}  // namespace b2h
