@@ -156,7 +156,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()
-    train_prec = "fp32" if args.precision == "auto" else args.precision
+    train_prec = "bf16" if args.precision == "auto" else args.precision
     fwd_prec = "bf16" if args.precision == "auto" else args.precision
 
     # ---------------- headline: training step, batch 256 x 64 per GPU ----------------
@@ -252,7 +252,7 @@ def main():
                        "global_batch": B_TRAIN * world, "frames_per_window": T, "conv_channels": C,
                        "parallelism": f"dp{world}", "cuda_graph": graphed,
                        "l2": f"{N_SLOTS} resident batches rotated ({N_SLOTS * (h2d) / 1e6:.0f} MB inputs + "
-                             f"{_lib.workspace_bytes(B_TRAIN, T, 24, C, 0, 0) / 1e6:.0f} MB gradient partials) > 126 MB L2"},
+                             f"{_lib.workspace_bytes(B_TRAIN, T, 24, C, 0, _lib.PRECISIONS[train_prec]) / 1e6:.0f} MB gradient partials) > 126 MB L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "final_loss": final_loss}
 
     if rank == 0 and world == 1:
@@ -282,7 +282,7 @@ def main():
         if os.path.isfile(tpath):
             traffic = json.load(open(tpath)).get("train_kernel_dram_bytes_per_launch")
         line["roofline"] = {"bound": "tensor", "achieved": tfl, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tfl / pk["tflops"],
-                            "traffic": traffic, "kernel": "conv_fp32_kernel<train>" if train_prec == "fp32" else "conv_tc_train",
+                            "traffic": traffic, "kernel": "conv_fp32_kernel<train>" if train_prec == "fp32" else "conv_tc_tile_kernel<train>",
                             "kernel_ms": k_ms, "algorithmic_flop_per_launch": TRAIN_FLOP_PER_WINDOW * B_TRAIN,
                             "peak_source": pk["source"] + ", bf16 dense sustained",
                             "note": "back-to-back launches (launch gaps included); per-launch device time is in profiles/"}

@@ -90,6 +90,23 @@ __host__ __device__ inline int gp_index_of_flat(const Geo& g, int i) {
   return base + (k * g.cout[l] + co) * g.kp[l] + ci;
 }
 
+// GP index -> flat parameter index (-1 for the padding slots of the GP layout)
+__host__ __device__ inline int flat_index_of_gp(const Geo& g, int j) {
+  int l = 0, base = 0;
+  for (int q = 0; q < 4; ++q) {
+    const int sz = gp_layer_size(g, q);
+    if (j >= base + sz && q < 3) { base += sz; l = q + 1; }
+    else break;
+  }
+  const int rel = j - base;
+  const int wsz = B2H_KW * g.cout[l] * g.kp[l];
+  if (rel >= wsz) { const int b = rel - wsz; return b < g.cout[l] ? g.b_off[l] + b : -1; }
+  const int k = rel / (g.cout[l] * g.kp[l]);
+  const int r2 = rel - k * g.cout[l] * g.kp[l];
+  const int co = r2 / g.kp[l], ci = r2 - co * g.kp[l];
+  return ci < g.cin[l] ? g.w_off[l] + (co * g.cin[l] + ci) * B2H_KW + k : -1;
+}
+
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 void count_launch(int n = 1);

@@ -37,19 +37,34 @@ __global__ void pack_kernel(const float* __restrict__ params, char* packed, Geo 
   if (i < g.P) scatter_packed(g, packed, i, params[i]);
 }
 
-// grads[i] = sum_c partials[c][i];  loss = sum_c loss_partials[c]   (fixed order -> deterministic)
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int nparts, int gp_layout, Geo g,
-                                       float* __restrict__ grads, const float* __restrict__ loss_partials,
-                                       float* __restrict__ loss_out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < g.P) {
-    // gp_layout: the tensor-core kernel writes [k][co][ci_pad] rows (coalesced); FFMA kernel writes flat order
-    const int src = gp_layout ? gp_index_of_flat(g, i) : i;
-    const size_t stride = gp_layout ? (size_t)gp_total(g) : (size_t)g.P;
-    float s = 0.f;
-    for (int c = 0; c < nparts; ++c) s += partials[(size_t)c * stride + src];
-    grads[i] = s;
+// Cross-CTA partial sum, shared by the reduce and the Adam kernel.  A block owns 32 consecutive slots of the
+// partial layout (coalesced 128-B rows); its 8 warps each sum every 8th CTA slice, then combine through smem.
+// Fixed order -> deterministic.  Returns the total in warp 0 (all lanes), garbage elsewhere.
+__device__ __forceinline__ float block_partial_sum(const float* __restrict__ partials, int nparts, size_t stride, int j, int nj,
+                                                   float (*red)[32]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (j < nj) {
+    int c = warp;
+    for (; c + 24 < nparts; c += 32) {
+      s0 += partials[(size_t)c * stride + j];
+      s1 += partials[(size_t)(c + 8) * stride + j];
+      s2 += partials[(size_t)(c + 16) * stride + j];
+      s3 += partials[(size_t)(c + 24) * stride + j];
+    }
+    for (; c < nparts; c += 8) s0 += partials[(size_t)c * stride + j];
   }
+  red[warp][lane] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  float s = 0.f;
+  if (warp == 0) {
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][lane];
+  }
+  return s;
+}
+
+__device__ __forceinline__ void loss_partial_sum(const float* __restrict__ loss_partials, int nparts, float* __restrict__ loss_out) {
   if (blockIdx.x == 0 && threadIdx.x < 32 && loss_out) {
     float s = 0.f;
     for (int c = threadIdx.x; c < nparts; c += 32) s += loss_partials[c];
@@ -57,6 +72,21 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (threadIdx.x == 0) *loss_out = s;
   }
+}
+
+// grads[i] = sum_c partials[c][slot(i)];  loss = sum_c loss_partials[c]
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int nparts, int gp_layout, Geo g,
+                                                              float* __restrict__ grads, const float* __restrict__ loss_partials,
+                                                              float* __restrict__ loss_out) {
+  __shared__ float red[8][32];
+  const int nj = gp_layout ? gp_total(g) : g.P;
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const float s = block_partial_sum(partials, nparts, (size_t)nj, j, nj, red);
+  if (threadIdx.x < 32 && j < nj) {
+    const int i = gp_layout ? flat_index_of_gp(g, j) : j;
+    if (i >= 0) grads[i] = s;
+  }
+  loss_partial_sum(loss_partials, nparts, loss_out);
 }
 
 struct AdamArgs {
@@ -72,8 +102,8 @@ struct AdamArgs {
 // torch.optim.Adam single-tensor update (defaults: amsgrad=False, weight_decay=0, maximize=False):
 //   m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, 1-b2);
 //   denom = v.sqrt()/sqrt(1-b2^t) + eps;  p.addcdiv_(m, denom, value=-lr/(1-b1^t))
-__global__ void adam_kernel(AdamArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
+  __shared__ float red[8][32];
   __shared__ float s_step_size, s_inv_bc2_sqrt;
   if (a.step_dev) {   // bias corrections from the device-side step counter (graph replay)
     if (threadIdx.x == 0) {
@@ -85,27 +115,28 @@ __global__ void adam_kernel(AdamArgs a) {
     a.step_size = s_step_size;
     a.inv_bc2_sqrt = s_inv_bc2_sqrt;
   }
-  if (i < a.n) {
-    float gr = 0.f;
-    const int src = a.gp_layout ? gp_index_of_flat(a.g, (int)i) : (int)i;
-    const size_t stride = a.gp_layout ? (size_t)gp_total(a.g) : (size_t)a.n;
-    for (int c = 0; c < a.nparts; ++c) gr += a.grads[(size_t)c * stride + src];
-    gr *= a.grad_scale;
-    float m = a.m[i], v = a.v[i], p = a.params[i];
-    m = fmaf(gr - m, a.one_minus_b1, m);
-    v = fmaf(a.one_minus_b2 * gr, gr, v * a.beta2);
-    const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
-    p = p - a.step_size * (m / denom);
-    a.m[i] = m; a.v[i] = v; a.params[i] = p;
-    if (a.packed) scatter_packed(a.g, a.packed, (int)i, p);
+  const int nj = a.gp_layout ? gp_total(a.g) : (int)a.n;
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  float gr;
+  if (a.nparts == 1) {            // already-reduced flat gradient (modular / data-parallel path)
+    gr = (j < nj && threadIdx.x < 32) ? a.grads[j] : 0.f;
+  } else {
+    gr = block_partial_sum(a.grads, a.nparts, (size_t)nj, j, nj, red);
   }
-  if (blockIdx.x == 0 && threadIdx.x < 32 && a.loss_out) {
-    float s = 0.f;
-    for (int c = threadIdx.x; c < a.nparts; c += 32) s += a.loss_partials[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (threadIdx.x == 0) *a.loss_out = s;
+  if (threadIdx.x < 32 && j < nj) {
+    const int i = a.gp_layout ? flat_index_of_gp(a.g, j) : j;
+    if (i >= 0) {
+      gr *= a.grad_scale;
+      float m = a.m[i], v = a.v[i], p = a.params[i];
+      m = fmaf(gr - m, a.one_minus_b1, m);
+      v = fmaf(a.one_minus_b2 * gr, gr, v * a.beta2);
+      const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
+      p = p - a.step_size * (m / denom);
+      a.m[i] = m; a.v[i] = v; a.params[i] = p;
+      if (a.packed) scatter_packed(a.g, a.packed, i, p);
+    }
   }
+  loss_partial_sum(a.loss_partials, a.nparts, a.loss_out);
 }
 
 __global__ void mask_output_kernel(float* __restrict__ y, const int32_t* __restrict__ lengths, int B, int T, int row) {
@@ -176,7 +207,8 @@ int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t st
 
 int launch_reduce(const float* partials, int nparts, int gp_layout, const Geo& g, float* grads, const float* loss_partials,
                   float* loss_out, cudaStream_t stream) {
-  reduce_partials_kernel<<<(g.P + 255) / 256, 256, 0, stream>>>(partials, nparts, gp_layout, g, grads, loss_partials, loss_out);
+  const int nj = gp_layout ? gp_total(g) : g.P;
+  reduce_partials_kernel<<<(nj + 31) / 32, 256, 0, stream>>>(partials, nparts, gp_layout, g, grads, loss_partials, loss_out);
   count_launch();
   return check_launch("reduce_partials_kernel");
 }
@@ -195,7 +227,9 @@ int launch_adam(float* params, const float* grads, int nparts, int gp_layout, fl
   a.packed = reinterpret_cast<char*>(packed); a.g = g;
   a.loss_partials = loss_partials; a.loss_out = loss_out;
   a.lr_d = lr; a.beta1_d = beta1; a.beta2_d = beta2; a.step_dev = step_dev;
-  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a);
+  const int64_t nj = gp_layout ? (int64_t)gp_total(g) : n;
+  if (nparts == 1) adam_kernel<<<(unsigned)((nj + 31) / 32), 32, 0, stream>>>(a);
+  else adam_kernel<<<(unsigned)((nj + 31) / 32), 256, 0, stream>>>(a);
   count_launch();
   return check_launch("adam_kernel");
 }

