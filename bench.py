@@ -268,11 +268,18 @@ def main():
 
         for i in range(10):
             train_kernel_only(i % N_SLOTS)
-        reps = 200
         torch.cuda.synchronize()
+        kgraph = torch.cuda.CUDAGraph()                       # graph replay: device time, not Python launch rate
+        with torch.cuda.graph(kgraph):
+            for i in range(N_SLOTS):
+                train_kernel_only(i)
+        kgraph.replay()
+        torch.cuda.synchronize()
+        greps = 5
+        reps = greps * N_SLOTS
         ev0.record()
-        for i in range(reps):
-            train_kernel_only(i % N_SLOTS)
+        for _ in range(greps):
+            kgraph.replay()
         ev1.record()
         torch.cuda.synchronize()
         k_ms = ev0.elapsed_time(ev1) / reps
@@ -285,7 +292,7 @@ def main():
                             "traffic": traffic, "kernel": "conv_fp32_kernel<train>" if train_prec == "fp32" else "conv_tc_tile_kernel<train>",
                             "kernel_ms": k_ms, "algorithmic_flop_per_launch": TRAIN_FLOP_PER_WINDOW * B_TRAIN,
                             "peak_source": pk["source"] + ", bf16 dense sustained",
-                            "note": "back-to-back launches (launch gaps included); per-launch device time is in profiles/"}
+                            "note": "CUDA-graph replay of the kernel alone over the rotating batches (inter-kernel gaps included); per-launch device time is in profiles/"}
 
         if not args.skip_extras:
             # ---------------- config 2: forward, batch 512 x 64, bf16 tensor-core path ----------------

@@ -142,6 +142,10 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
     if (loss_kind != B2H_LOSS_L1 && loss_kind != B2H_LOSS_CONFL1) { set_error("%s: bad loss_kind %d", who, loss_kind); return B2H_EINVAL; }
     if (loss_kind == B2H_LOSS_CONFL1 && !conf) { set_error("%s: confL1 needs scores", who); return B2H_EINVAL; }
   } else if (!d_y) { set_error("%s: null d_y", who); return B2H_EINVAL; }
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(target) & 15) || (reinterpret_cast<uintptr_t>(packed) & 15)) {
+    set_error("%s: x, target and packed must be 16-byte aligned", who);
+    return B2H_EALIGN;
+  }
   g = make_geo(n_in, C, pos_emb);
   nparts = train_nparts(g, B, T, precision);
   const int64_t stride = train_part_stride(g, T, precision);
@@ -239,6 +243,13 @@ extern "C" int b2h_tc_probe(const void* a_bf16, const void* b_bf16, float* out, 
   if (!a_bf16 || !b_bf16 || !out) { set_error("b2h_tc_probe: null pointer"); return B2H_EINVAL; }
   return launch_tc_probe(a_bf16, b_bf16, out, n, ksteps, shift, variant, (cudaStream_t)stream);
 }
+
+extern "C" int b2h_tc_bench(void* out_i64x2, int M, int N, int reps, int nacc, int mn_major, void* stream) {
+  if (!out_i64x2) { set_error("b2h_tc_bench: null pointer"); return B2H_EINVAL; }
+  return launch_tc_bench(reinterpret_cast<long long*>(out_i64x2), M, N, reps, nacc, mn_major, (cudaStream_t)stream);
+}
+
+extern "C" void b2h_debug_timing(void* dev_i64x128) { set_debug_timing(reinterpret_cast<long long*>(dev_i64x128)); }
 
 extern "C" int b2h_tc_status(void) { return tc_status_and_clear(); }
 

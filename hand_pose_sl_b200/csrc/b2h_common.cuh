@@ -25,6 +25,7 @@ struct Geo {
   int64_t wd_off[4];        // fp32 dgrad taps     Wd[k'][co][ci]           = W[co][ci][4-k']   (layers 2..4)
   int64_t tf_off[4];        // bf16 UMMA B operand, forward  (blocks of [2][N][8])
   int64_t td_off[4];        // bf16 UMMA B operand, dgrad    (layers 2..4)
+  int64_t bias_off;         // fp32 [4][64] zero-padded biases (one 1-KB bulk copy into smem)
   int kp[4], np_[4];        // UMMA padded reduction (cin -> mult of 16) and N (cout -> mult of 16), forward
   int64_t packed_bytes;
 };
@@ -53,6 +54,7 @@ __host__ __device__ inline Geo make_geo(int n_in, int C, int pos_emb) {
     g.td_off[l] = b;
     if (l > 0) { b += (int64_t)B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2; b = (b + 127) / 128 * 128; }
   }
+  g.bias_off = b; b += 4 * 64 * 4;
   g.packed_bytes = b;
   return g;
 }
@@ -149,6 +151,8 @@ int launch_tc_tile_fwd(const void* x, int x_dtype, const float* params, const ch
                        int B, int T, int apply_mask, float out_scale, const Geo& g, cudaStream_t stream);
 int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream);
 
+void set_debug_timing(long long* p);
+int launch_tc_bench(long long* out, int M, int N, int reps, int nacc, int mn_major, cudaStream_t stream);
 int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t stream);
 int launch_reduce(const float* partials, int nparts, int gp_layout, const Geo& g, float* grads, const float* loss_partials,
                   float* loss_out, cudaStream_t stream);

@@ -350,4 +350,65 @@ int tc_status_and_clear() {
 
 }  // namespace b2h
 
+namespace b2h {
+using namespace tc;
+// ------------------------------------------------------------------------------------------------
+// Microbenchmark (bring-up aid): cycles per tcgen05.mma for a given shape, issued back to back by one
+// thread, rotating over `nacc` accumulators.  out[0] = cycles from first issue to completion,
+// out[1] = cycles spent in the issue loop alone.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) tc_bench_kernel(long long* out, int M, int N, int reps, int nacc, int mn_major, int rows) {
+  extern __shared__ __align__(128) unsigned char bsm[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  for (int i = tid; i < 64 * 1024 / 16; i += 128) reinterpret_cast<uint4*>(bsm)[i] = make_uint4(0, 0, 0, 0);
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_slot;
+  long long t0 = 0, t1 = 0;
+  const int nissue = nacc >> 8;          // upper bits: number of issuing warps (each with its own accumulators)
+  nacc &= 255;
+  if (tid == 0) { mbar_init(&bar, nissue > 0 ? nissue : 1); fence_barrier_init(); }
+  __syncthreads();
+  if (warp < (nissue > 0 ? nissue : 1)) {
+    if (elect_one()) {
+      const uint32_t a0 = smem_u32(bsm), b0 = smem_u32(bsm + 32 * 1024);
+      const uint32_t CH = rows * 16;
+      const uint64_t ad = mn_major ? make_smem_desc(a0, 128, CH) : make_smem_desc(a0, CH, 128);
+      const uint64_t bd = mn_major ? make_smem_desc(b0, 128, CH) : make_smem_desc(b0, CH, 128);
+      const uint32_t idesc = make_idesc_bf16(M, N, mn_major, mn_major);
+      const uint32_t dbase = tbase + warp * nacc * N;
+      t0 = clock64();
+      for (int r = 0; r < reps; ++r) umma_bf16(dbase + (r % nacc) * N, ad + (uint64_t)(r & 3), bd, idesc, 1);
+      t1 = clock64();
+      umma_commit(&bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar, 0, 40);
+  const long long t2 = clock64();
+  if (warp == 0 && t0 != 0) { out[0] = t2 - t0; out[1] = t1 - t0; }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+int launch_tc_bench(long long* out, int M, int N, int reps, int nacc, int mn_major, cudaStream_t stream) {
+  if ((M != 64 && M != 128) || N < 8 || N > 256 || (N % (M == 64 ? 8 : 16)) || reps < 1 || (nacc & 255) < 1 || (nacc & 255) * N * ((nacc >> 8) > 0 ? (nacc >> 8) : 1) > 512 || (nacc >> 8) > 4) {
+    set_error("b2h_tc_bench: bad arguments");
+    return B2H_EINVAL;
+  }
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(tc_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+  tc_bench_kernel<<<1, 128, 64 * 1024, stream>>>(out, M, N, reps, nacc, mn_major, 136);
+  count_launch();
+  return check_launch("tc_bench_kernel");
+}
+}  // namespace b2h
+
 #include "b2h_train_tc.cuh"

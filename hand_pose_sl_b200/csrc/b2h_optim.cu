@@ -16,7 +16,10 @@ __device__ __forceinline__ void scatter_packed(const Geo& g, char* packed, int i
 #pragma unroll
   for (int q = 1; q < 4; ++q)
     if (i >= g.w_off[q]) l = q;
-  if (i >= g.b_off[l]) return;  // biases are read from the flat buffer directly
+  if (i >= g.b_off[l]) {        // bias: also kept zero-padded [4][64] for the tensor-core kernels' smem copy
+    if (i - g.b_off[l] < 64) reinterpret_cast<float*>(packed + g.bias_off)[l * 64 + (i - g.b_off[l])] = v;
+    return;
+  }
   const int cin = g.cin[l], cout = g.cout[l];
   const int rel = i - g.w_off[l];
   const int co = rel / (cin * B2H_KW);

@@ -10,17 +10,24 @@
 // Tile geometry.  A tile is 128 TMEM lanes of output rows made of `nhalf` independent row segments:
 //   mode B (T <= 64): two segments of 64 rows, one M=64 MMA each (TMEM lanes 32q+i and 32q+16+i), every
 //                     segment holding g = floor(66/(T+2)) whole windows -> T=64: 2 windows per tile, no
-//                     padded-row waste;
+//                     padded-row waste; the two segments are issued by two different warps;
 //   mode A (64 < T <= 126): one segment of 128 rows, M=128, one window.
 // A segment lives in shared memory as [2 zero rows][window][2 zero rows][window]...[zero rows] in the
-// no-swizzle K-major canonical layout [channel/8][row][8 ch] (16-B rows), so conv tap k is a +16*k byte
-// shift of the A descriptor and the SAME buffer also serves, read as an MN-major operand, as A (dZ^T) or
-// B (layer input) of the weight-gradient GEMM (reduction over frames).
+// no-swizzle K-major canonical layout [channel/8][row][8 ch] (16-B rows), so conv tap k is a +k change of
+// the A descriptor's start-address field and the SAME buffer also serves, read as an MN-major operand, as
+// A (dZ^T) or B (layer input) of the weight-gradient GEMM (reduction over frames).
 //
 // Per tile: F1 F2 F3 F4(+loss,+dY) | D4,W4 | D3,W3 | D2,W2 | W1.   F/D = conv GEMM + epilogue
 // (tcgen05.ld -> bias/ReLU or ReLU-mask -> bf16 -> st.shared); W = weight/bias-gradient GEMMs that keep
 // accumulating in TMEM across all tiles of the CTA (issued right after D so they run under D's epilogue) and
 // are read out once at the end into the CTA's slice of the partials workspace (deterministic 2-stage sum).
+//
+// Measured on B200: one tcgen05.mma costs >= ~25 (M=64) / ~40 (M=128) cycles whatever N <= 64 is, so the MMA
+// phases are instruction-count bound at C=30: descriptors are pre-encoded (one integer add per MMA) and the
+// two row segments are issued from two warps.
+// Data movement: weights + biases by 1-D TMA bulk copies (cp.async.bulk, once per CTA), the target tile by bulk
+// copies (prefetched at tile start), the prediction tile by bulk stores; inputs are prefetched into registers
+// one tile ahead (fp32 -> bf16 conversion happens on the way to shared memory).
 #pragma once
 
 namespace b2h {
@@ -31,9 +38,10 @@ struct TcTileArgs {
   const float* target; const float* conf; const float* d_y; const int32_t* lengths;
   const float* params; const char* packed;
   float* y;               // forward output / masked prediction (nullable in train mode)
-  float* partials;        // [grid][GP]  (gradient-partial layout, see gp_* below)
+  float* partials;        // [grid][GP]  (gradient-partial layout, b2h_common.cuh gp_*)
   float* loss_partials;   // [grid]
   long long* step_dev;
+  long long* dbg;         // nullable: CTA 0 / thread 0 writes clock64() phase stamps here (b2h_debug_timing)
   int B, T, loss_kind, apply_mask, mode;   // mode 0 = forward only, 1 = train (loss inside), 2 = backward of given d_y
   float out_scale;
   int n_tiles, nhalf, MB, HR, gh;          // tile geometry
@@ -46,7 +54,7 @@ constexpr int kWgCol = 64;        // weight-gradient accumulators: 2 layer pairs
 constexpr int kWgPairCols = 5 * 32 + 8;
 
 struct TileSmem {   // byte offsets into dynamic smem
-  int g0, g1, x, a1, a2, a3, ones, wf[4], wd[4], total;
+  int g0, g1, x, a1, a2, a3, ones, ys, wf[4], wd[4], total;
 };
 
 __host__ __device__ inline TileSmem tile_smem_layout(const Geo& g, int rows, bool train) {
@@ -62,6 +70,7 @@ __host__ __device__ inline TileSmem tile_smem_layout(const Geo& g, int rows, boo
   s.a2 = o; o += (g.kp[1] / 8) * CH;
   s.a3 = o; o += train ? (g.kp[1] / 8) * CH : 0;
   s.ones = o; o += train ? CH : 0;
+  s.ys = o; o += 128 * B2H_COUT * 4;      // fp32 staging rows: y tile on its way out (fwd) / target tile on its way in (train)
   for (int l = 0; l < 4; ++l) { s.wf[l] = o; o += B2H_KW * g.kp[l] * g.np_[l] * 2; }
   for (int l = 0; l < 4; ++l) {
     s.wd[l] = o;
@@ -87,16 +96,41 @@ __device__ __forceinline__ void bf16x8_to_float(const uint4& q, float* f) {
   }
 }
 
+// pre-encoded shared-memory descriptor halves (SWIZZLE_NONE): lo = start>>4 | (LBO>>4)<<16, hi = SBO>>4 | version 1
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16); }
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// conv GEMM of one row segment: D[seg rows][N] = sum_{k,s} A[rows + k][16-ch step s] * B_{k,s}
+// a_lo already points at the segment's row 0; rows = buffer rows (chunk stride in 16-B units); b step = N*32 B
+__device__ __forceinline__ void issue_conv(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, int KS, int N,
+                                           int rows, uint32_t idesc) {
+  uint32_t acc = 0;
+#pragma unroll
+  for (int k = 0; k < B2H_KW; ++k) {
+    for (int s = 0; s < KS; ++s) {
+      umma_bf16(d_tmem, desc64(a_lo + 2 * s * rows + k, a_hi), desc64(b_lo + (k * KS + s) * 2 * N, b_hi), idesc, acc);
+      acc = 1;
+    }
+  }
+}
+
+#define B2H_STAMP() do { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 120) p.dbg[dbg_n++] = clock64(); } while (0)
+
 template <bool TRAIN>
 __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArgs p) {
+  int dbg_n = 0;
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bar;      // MMAs of the current phase complete (one arrival per issuing warp)
+  __shared__ __align__(8) uint64_t wbar;     // weights + biases landed (bulk async copies)
+  __shared__ __align__(8) uint64_t tbar;     // target tile landed (train)
   __shared__ uint32_t tmem_slot;
-  __shared__ float bias_s[4][64];
+  __shared__ __align__(16) float bias_s[4][64];
   __shared__ float red_s[4];
   const Geo& g = p.geo;
   const int T = p.T, MB = p.MB, HR = p.HR, nhalf = p.nhalf, gh = p.gh;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform
   const int rows = nhalf * HR;
   const int CH = rows * 16;
   const TileSmem L = tile_smem_layout(g, rows, TRAIN);
@@ -107,6 +141,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   unsigned char* A2 = smem + L.a2;
   unsigned char* A3 = smem + L.a3;
   unsigned char* ONES = smem + L.ones;
+  float* YS = reinterpret_cast<float*>(smem + L.ys);
+  B2H_STAMP();   // kernel start
 
   // this thread's row: TMEM lane == tid
   const int hh = (nhalf == 2) ? ((tid >> 4) & 1) : 0;
@@ -114,29 +150,60 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   const int row = hh * HR + 2 + m;
   const int wj = m / (T + 2), t = m - wj * (T + 2);
   const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const int srow = hh * MB + m;                  // row of this thread in the fp32 staging tile
+  const bool bulk_io = (T & 1) == 0;             // T*168 B and the staging row offsets are 16-B multiples
+  const int wpt = nhalf * gh;                    // windows per tile
+  const int nissue = nhalf;                      // issuing warps: one per row segment
+  const uint32_t idesc_M = (nhalf == 2) ? 64 : 128;
+  const int n_in = g.n_in;
+  const bool fast_in = (g.pos_emb == 0) && ((n_in & 7) == 0) && n_in <= 24 * 1 + 8;   // <= 4 chunks, register prefetch
+  const int cpr = n_in >> 3;
+
+  // ---- input prefetch registers (one tile ahead) ----
+  float4 xf[8];
+  uint4 xb[4];
+  auto prefetch_x = [&](int tile) {
+    const int gw = tile * wpt + hh * gh + wj;
+    const bool valid = (t < T) && (wj < gh) && (gw < p.B) && tile < p.n_tiles;
+    if (!fast_in || !valid) return;
+    if (p.x_dtype == B2H_DT_F32) {
+      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + ((size_t)gw * T + t) * n_in);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < 2 * cpr) xf[c] = __ldg(src + c);
+    } else {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + ((size_t)gw * T + t) * n_in);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < cpr) xb[c] = __ldg(src + c);
+    }
+  };
+  prefetch_x(blockIdx.x);
 
   if (warp == 0) tmem_alloc(&tmem_slot, TRAIN ? 512 : 64);
-  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
-  if (TRAIN && p.step_dev && blockIdx.x == 0 && tid == 0) *p.step_dev += 1;
-  // weights (packed bf16 UMMA blocks) -> smem, once per CTA
-  for (int l = 0; l < 4; ++l) {
-    const int nb = B2H_KW * g.kp[l] * g.np_[l] * 2;
-    const uint4* src = reinterpret_cast<const uint4*>(p.packed + g.tf_off[l]);
-    uint4* dst = reinterpret_cast<uint4*>(smem + L.wf[l]);
-    for (int i = tid; i < nb / 16; i += kTileThreads) dst[i] = __ldg(src + i);
-    if (TRAIN && l > 0) {
-      const int nd = B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2;
-      const uint4* s2 = reinterpret_cast<const uint4*>(p.packed + g.td_off[l]);
-      uint4* d2 = reinterpret_cast<uint4*>(smem + L.wd[l]);
-      for (int i = tid; i < nd / 16; i += kTileThreads) d2[i] = __ldg(s2 + i);
+  if (tid == 0) {
+    mbar_init(&bar, nissue);
+    mbar_init(&wbar, 1);
+    mbar_init(&tbar, 1);
+    fence_barrier_init();
+    // weights (packed bf16 UMMA blocks) + zero-padded biases -> smem once per CTA: 1-D bulk async copies (TMA engine)
+    // that run under the buffer zeroing and the first tile's input staging; completion is signalled on wbar.
+    uint32_t total = 4 * 64 * 4;
+    for (int l = 0; l < 4; ++l) {
+      total += B2H_KW * g.kp[l] * g.np_[l] * 2;
+      if (TRAIN && l > 0) total += B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2;
+    }
+    mbar_arrive_expect_tx(&wbar, total);
+    bulk_g2s(&bias_s[0][0], p.packed + g.bias_off, 4 * 64 * 4, &wbar);
+    for (int l = 0; l < 4; ++l) {
+      bulk_g2s(smem + L.wf[l], p.packed + g.tf_off[l], B2H_KW * g.kp[l] * g.np_[l] * 2, &wbar);
+      if (TRAIN && l > 0)
+        bulk_g2s(smem + L.wd[l], p.packed + g.td_off[l], B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2, &wbar);
     }
   }
-  for (int i = tid; i < 4 * 64; i += kTileThreads) {
-    const int l = i >> 6, c = i & 63;
-    bias_s[l][c] = (c < g.cout[l]) ? __ldg(p.params + g.b_off[l] + c) : 0.0f;
-  }
+  if (TRAIN && p.step_dev && blockIdx.x == 0 && tid == 0) *p.step_dev += 1;
   {  // zero every activation / gradient buffer once: pad rows and pad channels stay zero
-    const int act_bytes = L.wf[0];
+    const int act_bytes = L.ys;
     uint4* z = reinterpret_cast<uint4*>(smem);
     const uint4 zero = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < act_bytes / 16; i += kTileThreads) z[i] = zero;
@@ -145,11 +212,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
-  uint32_t phase = 0;
+  uint32_t phase = 0, tphase = 0;
   float loss_acc = 0.0f;
-  bool wg_started = false;
-  const int wpt = nhalf * gh;                      // windows per tile
-  const uint32_t idesc_M = (nhalf == 2) ? 64 : 128;
+  bool wg_started = false, weights_ready = false;
+  B2H_STAMP();   // setup done
+
+  // descriptor constants
+  const uint32_t hi_k = desc_hi(128);            // K-major operands: SBO = 128 B (8-row groups contiguous)
+  const uint32_t hi_mn = desc_hi((uint32_t)CH);  // MN-major operands: SBO = chunk stride
+  const uint32_t acc_d = tbase + kAccCol;
 
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int wbase = tile * wpt;
@@ -158,22 +229,37 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
     int len = T;
     if (valid && p.lengths) { len = p.lengths[gw]; len = len < 0 ? 0 : (len > T ? T : len); }
 
+    const bool tgt_smem = TRAIN && p.mode == 1 && bulk_io;
+    if (tid == 0) {
+      if (!TRAIN) bulk_wait_read0();              // previous tile's y stores have read the staging tile
+      if (tgt_smem) {                             // target rows of this tile's windows -> staging tile (TMA bulk loads)
+        int nw = p.B - wbase; nw = nw > wpt ? wpt : nw;
+        fence_proxy_async_smem();
+        mbar_arrive_expect_tx(&tbar, (uint32_t)nw * T * B2H_COUT * 4);
+        for (int w = 0; w < nw; ++w) {
+          const int h = w / gh, j = w - h * gh;
+          bulk_g2s(YS + (size_t)(h * MB + j * (T + 2)) * B2H_COUT, p.target + (size_t)(wbase + w) * T * B2H_COUT,
+                   (uint32_t)T * B2H_COUT * 4, &tbar);
+        }
+      }
+    }
     // ---- stage inputs: one thread per row, (n_in) channels NWC -> X [chunk][row][8] bf16 ----
     {
-      const int n_in = g.n_in, pe = g.pos_emb;
+      const int pe = g.pos_emb;
       const int nch0 = g.kp[0] / 8;
-      if (valid && pe == 0 && (n_in & 7) == 0) {
-        const int cpr = n_in >> 3;
+      if (valid && fast_in) {
         if (p.x_dtype == B2H_DT_F32) {
-          const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + ((size_t)gw * T + t) * n_in);
-          for (int c8 = 0; c8 < cpr; ++c8) {
-            const float4 lo = __ldg(src + 2 * c8), hi = __ldg(src + 2 * c8 + 1);
-            const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            store8_bf16(X, CH, row, c8, v);
-          }
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8)
+            if (c8 < cpr) {
+              const float4 lo = xf[2 * c8], hi = xf[2 * c8 + 1];
+              const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+              store8_bf16(X, CH, row, c8, v);
+            }
         } else {
-          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + ((size_t)gw * T + t) * n_in);
-          for (int c8 = 0; c8 < cpr; ++c8) *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = __ldg(src + c8);
+#pragma unroll
+          for (int c8 = 0; c8 < 4; ++c8)
+            if (c8 < cpr) *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = xb[c8];
         }
       } else if (valid) {
         for (int c8 = 0; c8 < nch0; ++c8) {
@@ -202,36 +288,36 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         *reinterpret_cast<uint4*>(ONES + (size_t)row * 16) = o;
       }
     }
+    prefetch_x(tile + gridDim.x);                 // next tile's rows travel while this tile computes
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    B2H_STAMP();   // staging done
+    if (!weights_ready) { mbar_wait(&wbar, 0, 19); weights_ready = true; }
+    B2H_STAMP();   // weights landed
 
     // =========================== forward: 4 conv layers ===========================
     for (int l = 0; l < 4; ++l) {
       unsigned char* bin = (l == 0) ? X : (l == 1) ? A1 : (l == 2) ? A2 : (TRAIN ? A3 : A1);
       unsigned char* bout = (l == 0) ? A1 : (l == 1) ? A2 : (TRAIN ? A3 : A1);
       const int KS = g.kp[l] >> 4, N = g.np_[l];
-      if (tid == 0) {
-        const uint32_t idesc = make_idesc_bf16(idesc_M, N, 0, 0);
-        const uint32_t a_base = smem_u32(bin), w_base = smem_u32(smem + L.wf[l]);
-        for (int h = 0; h < nhalf; ++h) {
-          uint32_t acc = 0;
-          for (int k = 0; k < B2H_KW; ++k)
-            for (int s = 0; s < KS; ++s) {
-              // output row 2+m of segment h reads input row m+k
-              const uint64_t ad = make_smem_desc(a_base + (2 * s) * CH + (h * HR + k) * 16, CH, 128);
-              const uint64_t bd = make_smem_desc(w_base + (k * KS + s) * (N * 32), N * 16, 128);
-              umma_bf16(tbase + kAccCol + ((uint32_t)(h * 16) << 16), ad, bd, idesc, acc);
-              acc = 1;
-            }
+      if (warp < nissue) {
+        if (elect_one()) {
+          const uint32_t idesc = make_idesc_bf16(idesc_M, N, 0, 0);
+          // output row 2+m of segment h reads input row m+k  ->  start row = h*HR + k
+          const uint32_t a_lo = desc_lo(smem_u32(bin), (uint32_t)CH) + warp * HR;
+          const uint32_t b_lo = desc_lo(smem_u32(smem + L.wf[l]), (uint32_t)N * 16);
+          issue_conv(acc_d + ((uint32_t)(warp * 16) << 16), a_lo, hi_k, b_lo, hi_k, KS, N, rows, idesc);
+          umma_commit(&bar);
         }
-        umma_commit(&bar);
+        __syncwarp();
       }
-      __syncwarp();
+      B2H_STAMP();   // fwd layer: MMAs issued
       mbar_wait(&bar, phase, 20 + l);
       phase ^= 1;
       tc_fence_after();
+      B2H_STAMP();   // fwd layer: accumulator ready
       const uint32_t taddr = tbase + lane_addr + kAccCol;
       if (l < 3) {
         for (int c0 = 0; c0 < N; c0 += 16) {
@@ -252,13 +338,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           n_el = (float)len * (float)B2H_COUT;
           scale = (p.loss_kind == B2H_LOSS_L1) ? (1.0f / (float)p.B) / n_el : 1.0f / n_el;
           if (p.mode == 1) {
-            tg = p.target + ((size_t)gw * T + t) * B2H_COUT;
+            tg = tgt_smem ? YS + (size_t)srow * B2H_COUT : p.target + ((size_t)gw * T + t) * B2H_COUT;
             cf = p.conf ? p.conf + ((size_t)gw * T + t) * (B2H_COUT / 2) : nullptr;
           } else {
             dy = p.d_y + ((size_t)gw * T + t) * B2H_COUT;
           }
         }
-        float* yrow = (valid && p.y) ? p.y + ((size_t)gw * T + t) * B2H_COUT : nullptr;
+        const bool y_smem = !TRAIN && bulk_io;
+        float* yrow = (valid && p.y) ? (y_smem ? YS + (size_t)srow * B2H_COUT : p.y + ((size_t)gw * T + t) * B2H_COUT) : nullptr;
+        if (tgt_smem) { mbar_wait(&tbar, tphase, 18); tphase ^= 1; }
+        B2H_STAMP();   // layer-4 epilogue: target tile landed
         float sum = 0.f;
         for (int c0 = 0; c0 < N; c0 += 16) {
           uint32_t v[16];
@@ -278,7 +367,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
               if (yrow) *reinterpret_cast<float2*>(yrow + c) = make_float2(a, b);
               if (TRAIN && !masked) {
                 if (p.mode == 1) {
-                  const float2 tv = __ldg(reinterpret_cast<const float2*>(tg + c));
+                  const float2 tv = *reinterpret_cast<const float2*>(tg + c);
                   float da, db, s = 1.0f;
                   if (p.loss_kind == B2H_LOSS_L1) { da = a - tv.x; db = b - tv.y; }     // utils.py:422-426
                   else {
@@ -314,6 +403,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
+      if (!TRAIN && l == 3 && bulk_io && tid == 0 && p.y) {   // y tile -> global: one TMA bulk store per window
+        int nw = p.B - wbase; nw = nw > wpt ? wpt : nw;
+        for (int w = 0; w < nw; ++w) {
+          const int h = w / gh, j = w - h * gh;
+          bulk_s2g(p.y + (size_t)(wbase + w) * T * B2H_COUT, YS + (size_t)(h * MB + j * (T + 2)) * B2H_COUT, (uint32_t)T * B2H_COUT * 4);
+        }
+        bulk_commit();
+      }
+      B2H_STAMP();   // fwd layer: epilogue done
     }
     if (TRAIN && p.mode == 1 && tid == 0) loss_acc += red_s[0] + red_s[1] + red_s[2] + red_s[3];
 
@@ -324,50 +422,46 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         unsigned char* gz = ((3 - l) & 1) ? G1 : G0;          // dZ_l
         unsigned char* gnext = ((3 - l) & 1) ? G0 : G1;       // dZ_{l-1}
         unsigned char* ain = (l == 0) ? X : (l == 1) ? A1 : (l == 2) ? A2 : A3;   // layer l's input activation
-        if (tid == 0) {
-          if (l > 0) {  // dgrad: dA_{l-1}[r][ci] = sum_{k',co} dZ_l[r+k'-2][co] * W_l[co][ci][4-k']
-            const int KSd = round_up(g.cout[l], 16) >> 4, Nd = round_up(g.cin[l], 16);
-            const uint32_t idesc = make_idesc_bf16(idesc_M, Nd, 0, 0);
-            const uint32_t a_base = smem_u32(gz), w_base = smem_u32(smem + L.wd[l]);
-            for (int h = 0; h < nhalf; ++h) {
-              uint32_t acc = 0;
-              for (int k = 0; k < B2H_KW; ++k)
-                for (int s = 0; s < KSd; ++s) {
-                  const uint64_t ad = make_smem_desc(a_base + (2 * s) * CH + (h * HR + k) * 16, CH, 128);
-                  const uint64_t bd = make_smem_desc(w_base + (k * KSd + s) * (Nd * 32), Nd * 16, 128);
-                  umma_bf16(tbase + kAccCol + ((uint32_t)(h * 16) << 16), ad, bd, idesc, acc);
-                  acc = 1;
-                }
+        if (warp < nissue) {
+          if (elect_one()) {
+            if (l > 0) {  // dgrad: dA_{l-1}[r][ci] = sum_{k',co} dZ_l[r+k'-2][co] * W_l[co][ci][4-k']
+              const int KSd = round_up(g.cout[l], 16) >> 4, Nd = round_up(g.cin[l], 16);
+              const uint32_t idesc = make_idesc_bf16(idesc_M, Nd, 0, 0);
+              const uint32_t a_lo = desc_lo(smem_u32(gz), (uint32_t)CH) + warp * HR;
+              const uint32_t b_lo = desc_lo(smem_u32(smem + L.wd[l]), (uint32_t)Nd * 16);
+              issue_conv(acc_d + ((uint32_t)(warp * 16) << 16), a_lo, hi_k, b_lo, hi_k, KSd, Nd, rows, idesc);
+              umma_commit(&bar);
             }
-            umma_commit(&bar);
-          }
-          // wgrad: dW_l[k][co][ci] += sum_r dZ_l[r][co] * in_l[r+k-2][ci];  db_l[co] += sum_r dZ_l[r][co]
-          // A = dZ_l read MN-major (M = co, 8 chunks), B = in_l read MN-major (N = ci), K = 16 frames per MMA
-          {
-            const int Nw = g.kp[l];
-            const uint32_t idw = make_idesc_bf16(64, Nw, 1, 1), idb = make_idesc_bf16(64, 8, 1, 1);
-            const uint32_t a_base = smem_u32(gz), b_base = smem_u32(ain), o_base = smem_u32(ONES);
-            const uint32_t dcol = tbase + kWgCol + (l >> 1) * kWgPairCols + ((uint32_t)((l & 1) * 16) << 16);
-            const uint32_t accw = wg_started ? 1u : 0u;
-            for (int h = 0; h < nhalf; ++h)
-              for (int s = 0; s < MB / 16; ++s) {
-                const uint32_t first = (h == 0 && s == 0) ? accw : 1u;
-                const uint32_t r0 = (h * HR + 2 + 16 * s) * 16;
-                const uint64_t ad = make_smem_desc(a_base + r0, 128, CH);
-                for (int k = 0; k < B2H_KW; ++k) {
-                  const uint64_t bd = make_smem_desc(b_base + r0 + (k - 2) * 16, 128, CH);
-                  umma_bf16(dcol + k * 32, ad, bd, idw, first);
+            // wgrad: dW_l[k][co][ci] += sum_r dZ_l[r][co] * in_l[r+k-2][ci];  db_l[co] += sum_r dZ_l[r][co]
+            // A = dZ_l read MN-major (M = co, 8 chunks), B = in_l read MN-major (N = ci), K = 16 frames per MMA.
+            // The six accumulators (5 taps + bias) are split between the issuing warps (disjoint TMEM columns).
+            {
+              const int Nw = g.kp[l];
+              const uint32_t idw = make_idesc_bf16(64, Nw, 1, 1), idb = make_idesc_bf16(64, 8, 1, 1);
+              const uint32_t a_lo0 = desc_lo(smem_u32(gz), 128), b_lo0 = desc_lo(smem_u32(ain), 128), o_lo0 = desc_lo(smem_u32(ONES), 128);
+              const uint32_t dcol = tbase + kWgCol + (l >> 1) * kWgPairCols + ((uint32_t)((l & 1) * 16) << 16);
+              for (int h = 0; h < nhalf; ++h)
+                for (int s = 0; s < MB / 16; ++s) {
+                  const uint32_t first = (h == 0 && s == 0 && !wg_started) ? 0u : 1u;
+                  const uint32_t r0 = h * HR + 2 + 16 * s;           // rows (16-B units)
+                  const uint64_t ad = desc64(a_lo0 + r0, hi_mn);
+#pragma unroll
+                  for (int k = 0; k < B2H_KW + 1; ++k) {
+                    if ((k % nissue) != warp) continue;
+                    if (k < B2H_KW) umma_bf16(dcol + k * 32, ad, desc64(b_lo0 + r0 + k - 2, hi_mn), idw, first);
+                    else umma_bf16(dcol + 5 * 32, ad, desc64(o_lo0 + r0, hi_mn), idb, first);
+                  }
                 }
-                const uint64_t od = make_smem_desc(o_base + r0, 128, CH);
-                umma_bf16(dcol + 5 * 32, ad, od, idb, first);
-              }
-            if (l == 0) umma_commit(&bar);     // last MMAs of the tile: fence the buffers before restaging
+              if (l == 0) umma_commit(&bar);     // last MMAs of the tile: fence the buffers before restaging
+            }
           }
+          __syncwarp();
         }
-        __syncwarp();
+        B2H_STAMP();   // bwd layer: MMAs issued
         mbar_wait(&bar, phase, 30 + l);
         phase ^= 1;
         tc_fence_after();
+        B2H_STAMP();   // bwd layer: dgrad accumulator ready
         if (l > 0) {
           // dZ_{l-1} = dA_{l-1} * (a_{l-1} > 0)     (ReLU backward on the saved activation)
           const int Nd = round_up(g.cin[l], 16);
@@ -389,6 +483,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+        B2H_STAMP();   // bwd layer: epilogue done
       }
       wg_started = true;
     }
@@ -396,41 +491,44 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
 
   if (TRAIN) {
     // ---- read the weight / bias gradient accumulators out into this CTA's partial slice ----
+    // A layer pair shares its TMEM columns: lanes 32q+i hold layer 2p (co = 16q+i), lanes 32q+16+i layer 2p+1,
+    // so one tcgen05.ld per tap serves both layers and every lane has a row to store.
     float* part = p.partials + (size_t)blockIdx.x * gp_total(g);
-    if (!wg_started) {   // CTA had no tile (grid > n_tiles never happens, but keep the slice defined)
+    if (!wg_started) {
       for (int i = tid; i < gp_total(g); i += kTileThreads) part[i] = 0.0f;
     } else {
-      for (int l = 0; l < 4; ++l) {
-        // layer l's accumulators sit in TMEM lanes 32q + 16*(l&1) + i  <->  co = 16q + i
+      for (int pr = 0; pr < 2; ++pr) {
+        const int l = 2 * pr + (lane >> 4);
         const int co = warp * 16 + (lane & 15);
-        const bool mine = ((lane >> 4) == (l & 1)) && co < g.cout[l];
+        const bool mine = co < g.cout[l];
         const int Nw = g.kp[l];
         float* lp = part + gp_layer_off(g, l);
-        const uint32_t dcol = tbase + lane_addr + kWgCol + (l >> 1) * kWgPairCols;
-        for (int k = 0; k < B2H_KW; ++k)
-          for (int c0 = 0; c0 < Nw; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(dcol + k * 32 + c0, v);
-            tmem_ld_wait();
-            if (mine) {
-              float4* dst = reinterpret_cast<float4*>(lp + ((size_t)k * g.cout[l] + co) * Nw + c0);
+        const uint32_t dcol = tbase + lane_addr + kWgCol + pr * kWgPairCols;
+        uint32_t v[B2H_KW][32];
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                                     __uint_as_float(v[4 * q + 3]));
-            }
+        for (int k = 0; k < B2H_KW; ++k) tmem_ld32(dcol + k * 32, v[k]);
+        uint32_t vb[16];
+        tmem_ld16(dcol + 5 * 32, vb);      // 8 valid columns; column 0 holds db (ones sits in element 0)
+        tmem_ld_wait();
+        if (mine) {
+#pragma unroll
+          for (int k = 0; k < B2H_KW; ++k) {
+            float4* dst = reinterpret_cast<float4*>(lp + ((size_t)k * g.cout[l] + co) * Nw);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (q * 4 < Nw)
+                dst[q] = make_float4(__uint_as_float(v[k][4 * q]), __uint_as_float(v[k][4 * q + 1]), __uint_as_float(v[k][4 * q + 2]),
+                                     __uint_as_float(v[k][4 * q + 3]));
           }
-        {
-          uint32_t v[16];
-          tmem_ld16(dcol + 5 * 32, v);     // 8 valid columns; column 0 holds db (ones sits in element 0)
-          tmem_ld_wait();
-          if (mine) lp[B2H_KW * g.cout[l] * Nw + co] = __uint_as_float(v[0]);
+          lp[B2H_KW * g.cout[l] * Nw + co] = __uint_as_float(vb[0]);
         }
       }
     }
     if (tid == 0 && p.loss_partials)
       p.loss_partials[blockIdx.x] = (p.loss_kind == B2H_LOSS_L1) ? loss_acc / (float)p.B : loss_acc;
   }
+  if (!TRAIN && tid == 0) bulk_wait0();
+  B2H_STAMP();   // readout done
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tbase, TRAIN ? 512 : 64);
@@ -482,6 +580,8 @@ int launch_tc_tile(TcTileArgs& p, bool train, cudaStream_t stream) {
   return check_launch(train ? "conv_tc_tile_kernel<train>" : "conv_tc_tile_kernel<fwd>");
 }
 
+static long long* g_dbg_timing = nullptr;
+void set_debug_timing(long long* p) { g_dbg_timing = p; }
 
 bool tc_tile_ok(const Geo& g, int T, bool train) { return tc_tile_supported(g, T, train); }
 
@@ -490,6 +590,7 @@ int launch_tc_tile_fwd(const void* x, int x_dtype, const float* params, const ch
   TcTileArgs p{};
   p.x = x; p.x_dtype = x_dtype; p.params = params; p.packed = packed; p.lengths = lengths; p.y = y;
   p.B = B; p.T = T; p.apply_mask = apply_mask; p.mode = 0; p.out_scale = out_scale; p.geo = g;
+  p.dbg = g_dbg_timing;
   return launch_tc_tile(p, false, stream);
 }
 
@@ -499,6 +600,7 @@ int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream) {
   p.params = a.params; p.packed = a.packed; p.y = a.y; p.partials = a.partials; p.loss_partials = a.loss_partials;
   p.step_dev = a.step_dev; p.B = a.B; p.T = a.T; p.loss_kind = a.loss_kind; p.apply_mask = 1; p.mode = a.mode;
   p.out_scale = 1.0f; p.geo = a.geo;
+  p.dbg = g_dbg_timing;
   return launch_tc_tile(p, true, stream);
 }
 

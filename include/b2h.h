@@ -159,6 +159,14 @@ int b2h_tc_probe(const void* a_bf16, const void* b_bf16, float* out, int n, int 
  * gave up (the kernels never spin forever); reading clears it.  Synchronises the device. */
 int b2h_tc_status(void);
 
+/* Bring-up aid: cycles for `reps` back-to-back tcgen05.mma (bf16, K=16) of shape MxN rotating over `nacc`
+ * accumulators; out[0] = issue-to-completion cycles, out[1] = issue-loop cycles. */
+int b2h_tc_bench(void* out_i64x2, int M, int N, int reps, int nacc, int mn_major, void* stream);
+
+/* Bring-up aid: when set to a device buffer of 128 int64, CTA 0 of the tile kernels stamps clock64() at every
+ * phase boundary (setup, staging, per-layer issue / ready / epilogue); NULL switches it off. */
+void b2h_debug_timing(void* dev_i64x128);
+
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t b2h_launch_count(void);
 
