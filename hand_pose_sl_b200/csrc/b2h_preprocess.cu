@@ -56,8 +56,8 @@ struct PreArgs {
   const float* src[3];
   int64_t n_frames;
   const int64_t* win_start;
-  int n_win, T, pad_mode, dif, normalize, aligned;
-  float factor;
+  int n_win, T, pad_mode, dif, normalize, aligned, fastdiv;
+  float factor, rfactor;
   float* out[6];  // input_kp, input_conf, target_kp, target_conf, left_kp, left_conf
   int64_t* n_frames_out;
   __nv_bfloat16* input_bf16;
@@ -94,69 +94,106 @@ __device__ __forceinline__ float out_elem(const float* st, int a, int i, int r, 
   }
 }
 
+// Exact division by the normalisation factor without the generic div.rn sequence (whose special-operand
+// slow path is taken for every zero = undetected keypoint).  With rc = RN(1/c):  q = RN(x*rc),
+// r = x - q*c (exact, FMA), q' = RN(q + r*rc) is the correctly rounded x/c (Markstein) as long as nothing
+// over/underflows; outside that range the IEEE routine is used.  tests/test_gpu_preprocess.py checks the
+// identity for c = 1280 over ALL 2^32 float bit patterns on the device (b2h_verify_fastdiv).
+__device__ __forceinline__ float div_exact(float x, float c, float rc) {
+  const float ax = fabsf(x);
+  if (ax == 0.0f) return x;                 // (+-0)/c = +-0 for the positive factor (the FMA chain would lose -0)
+  if (ax < 1e30f && ax > 1e-30f) {
+    const float q = __fmul_rn(x, rc);
+    const float r = __fmaf_rn(-q, c, x);
+    return __fmaf_rn(r, rc, q);
+  }
+  return __fdiv_rn(x, c);
+}
+
+__global__ void verify_fastdiv_kernel(float c, float rc, unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32);
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const float x = __uint_as_float((unsigned)i);
+    const float a = div_exact(x, c, rc), b = __fdiv_rn(x, c);
+    const bool same = (__float_as_uint(a) == __float_as_uint(b)) || (a != a && b != b);
+    bad += same ? 0 : 1;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 // Gather table (built once per CTA in shared memory): for every output float4 of a 4-slot group, which array
-// it belongs to and, per element, where its source value and its reference (neck / wrist) value sit in the
-// staged tile.  The steady-state loop is then: LDS.128 (table) + 2 LDS + sub.rn + div.rn per element.
-//   entry: bits 0-9 src offset, 10-19 ref offset, bit 20 subtract ref, bit 21 divide by factor
-//   qinfo: bits 0-7 float4 index inside the array's 4-slot block, bits 8-10 array id
+// it belongs to and, per element, where its source value and its reference (neck / wrist, or a zero slot)
+// sit in the staged tile.  Arrays that are divided by the factor come first, so the steady-state loop has no
+// per-element flags:  LDS.128 (table) + 2 LDS + sub.rn [+ exact division] per element, one STG.128 per four.
+//   entry: bits 0-15 src offset, 16-31 ref offset          qinfo: bits 0-7 float4 index in the array block, 8-10 array
 template <int FMT>
-__device__ __forceinline__ uint32_t table_entry(int a, int i, int r, const PreArgs& p) {
+__device__ __forceinline__ uint32_t table_entry(int a, int i, int r, const PreArgs& p, int zero_slot) {
   using F = Fmt<FMT>;
-  // offsets are relative to the per-warp stage; recover them through the accessor on a null base
   const float* z = nullptr;
-  uint32_t src = 0, ref = 0, sub = 0, nrm = 0;
+  uint32_t src = 0, ref = (uint32_t)zero_slot;
   const int j = r >> 1, d = r & 1;
   switch (a) {
-    case 0: src = (uint32_t)(&F::body_ref(z, i, j, d) - z); ref = (uint32_t)(&F::body_ref(z, i, 1, d) - z); sub = p.dif; nrm = p.normalize; break;
+    case 0: src = (uint32_t)(&F::body_ref(z, i, j, d) - z); if (p.dif) ref = (uint32_t)(&F::body_ref(z, i, 1, d) - z); break;
     case 1: src = (uint32_t)(&F::body_ref(z, i, r, 2) - z); break;
-    case 2: src = (uint32_t)(&F::rh_ref(z, i, j, d) - z); ref = (uint32_t)(&F::body_ref(z, i, 4, d) - z); sub = p.dif; nrm = p.normalize; break;
+    case 2: src = (uint32_t)(&F::rh_ref(z, i, j, d) - z); if (p.dif) ref = (uint32_t)(&F::body_ref(z, i, 4, d) - z); break;
     case 3: src = (uint32_t)(&F::rh_ref(z, i, r, 2) - z); break;
-    case 4: src = (uint32_t)(&F::lh_ref(z, i, j, d) - z); nrm = p.normalize; break;
+    case 4: src = (uint32_t)(&F::lh_ref(z, i, j, d) - z); break;
     default: src = (uint32_t)(&F::lh_ref(z, i, r, 2) - z); break;
   }
-  return src | (ref << 10) | (sub << 20) | (nrm << 21);
+  return src | (ref << 16);
 }
 
 template <int FMT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) preprocess_kernel(PreArgs p) {
   using F = Fmt<FMT>;
   constexpr int kMaxQ = F::kBody * 3 + 126;             // float4 per 4-slot group over all six arrays
-  __shared__ __align__(16) float stage_all[kWarpsPerBlock][F::kStage];
+  constexpr int kZero = F::kStage;                      // 4 zero floats behind every warp's staged tile
+  __shared__ __align__(16) float stage_all[kWarpsPerBlock][F::kStage + 4];
   __shared__ __align__(16) uint32_t tab[kMaxQ * 4];
   __shared__ uint16_t qinfo[kMaxQ];
-  __shared__ int s_nq;
+  __shared__ int s_nq, s_nq_div;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float* st = stage_all[wib];
   const int64_t S = (int64_t)p.n_win * p.T;
   const int64_t n_groups = (S + 3) >> 2;
   const int n_out[6] = {F::kBody * 2, F::kBody, 42, 21, 42, 21};
 
-  // ---- build the gather table (arrays that are not requested are skipped) ----
+  // ---- build the gather table: divided arrays (keypoints) first, then pass-through arrays (confidences) ----
   {
+    const int order[6] = {0, 2, 4, 1, 3, 5};
     int qbase[7];
-    int acc = 0;
+    int acc = 0, ndiv = 0;
 #pragma unroll
-    for (int a = 0; a < 6; ++a) { qbase[a] = acc; acc += p.out[a] ? n_out[a] : 0; }
+    for (int o = 0; o < 6; ++o) {
+      const int a = order[o];
+      qbase[o] = acc;
+      acc += p.out[a] ? n_out[a] : 0;
+      if (o == 2) ndiv = p.normalize ? acc : 0;
+    }
     qbase[6] = acc;
-    if (threadIdx.x == 0) s_nq = acc;
+    if (threadIdx.x == 0) { s_nq = acc; s_nq_div = ndiv; }
     for (int q = threadIdx.x; q < acc; q += blockDim.x) {
-      int a = 0;
+      int o = 0;
 #pragma unroll
       for (int c = 1; c < 6; ++c)
-        if (q >= qbase[c]) a = c;
-      const int ql = q - qbase[a], n = n_out[a];
+        if (q >= qbase[c]) o = c;
+      const int a = order[o];
+      const int ql = q - qbase[o], n = n_out[a];
       qinfo[q] = (uint16_t)(ql | (a << 8));
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int idx = ql * 4 + e;
         const int i = idx / n, r = idx - i * n;
-        tab[q * 4 + e] = table_entry<FMT>(a, i, r, p);
+        tab[q * 4 + e] = table_entry<FMT>(a, i, r, p, kZero);
       }
     }
+    if (lane < 4) st[kZero + lane] = 0.0f;
   }
   __syncthreads();
-  const int nq = s_nq;
-  const float factor = p.factor;
+  const int nq = s_nq, nq_div = s_nq_div;
+  const float factor = p.factor, rfactor = p.rfactor;
+  const bool fastdiv = p.fastdiv != 0;
   const bool small = S < (int64_t)0x7fffffff;
 
   for (int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + wib; g < n_groups; g += (int64_t)gridDim.x * kWarpsPerBlock) {
@@ -247,11 +284,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) preprocess_kernel(PreArgs
         const uint32_t en[4] = {e4.x, e4.y, e4.z, e4.w};
         float v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float x = st[en[e] & 1023u];
-          if (en[e] & (1u << 20)) x = __fsub_rn(x, st[(en[e] >> 10) & 1023u]);   // utils.py:200 / :209
-          if (en[e] & (1u << 21)) x = __fdiv_rn(x, factor);                       // utils.py:186-188
-          v[e] = x;
+        for (int e = 0; e < 4; ++e) v[e] = __fsub_rn(st[en[e] & 0xFFFFu], st[en[e] >> 16]);   // utils.py:200 / :209 (x - 0 = x)
+        if (q < nq_div) {                                                                  // utils.py:186-188
+          if (fastdiv) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = div_exact(v[e], factor, rfactor);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = __fdiv_rn(v[e], factor);
+          }
         }
         const int qi = qinfo[q];
         const int a = qi >> 8, ql = qi & 255;
@@ -311,6 +352,13 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 using namespace b2h;
 
+extern "C" int b2h_verify_fastdiv(float factor, unsigned long long* mismatches_dev, void* stream) {
+  if (!mismatches_dev) { set_error("b2h_verify_fastdiv: null pointer"); return B2H_EINVAL; }
+  verify_fastdiv_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(factor, 1.0f / factor, mismatches_dev);
+  count_launch();
+  return check_launch("verify_fastdiv_kernel");
+}
+
 extern "C" int b2h_preprocess(const float* pose25, const float* hand_left, const float* hand_right, int64_t n_frames,
                               const int64_t* win_start, int n_win, int T, int pad_mode, float factor,
                               int dif_encoding, int normalize, float* input_kp, float* input_conf,
@@ -326,6 +374,7 @@ extern "C" int b2h_preprocess(const float* pose25, const float* hand_left, const
   p.src[0] = pose25; p.src[1] = hand_left; p.src[2] = hand_right;
   p.n_frames = n_frames; p.win_start = win_start; p.n_win = n_win; p.T = T; p.pad_mode = pad_mode;
   p.dif = dif_encoding; p.normalize = normalize; p.factor = factor;
+  p.rfactor = 1.0f / factor; p.fastdiv = (factor == 1280.0f) ? 1 : 0;   // the reference's factor (run.py:90): verified exhaustively
   p.out[0] = input_kp; p.out[1] = input_conf; p.out[2] = target_kp; p.out[3] = target_conf;
   p.out[4] = left_kp; p.out[5] = left_conf;
   p.n_frames_out = n_frames_out; p.input_bf16 = reinterpret_cast<__nv_bfloat16*>(input_kp_bf16);
@@ -350,6 +399,7 @@ extern "C" int b2h_preprocess_h5(const float* rows150, int64_t n_frames, const i
   p.src[0] = rows150; p.src[1] = nullptr; p.src[2] = nullptr;
   p.n_frames = n_frames; p.win_start = win_start; p.n_win = n_win; p.T = T; p.pad_mode = pad_mode;
   p.dif = dif_encoding; p.normalize = normalize; p.factor = factor;
+  p.rfactor = 1.0f / factor; p.fastdiv = (factor == 1280.0f) ? 1 : 0;   // the reference's factor (run.py:90): verified exhaustively
   p.out[0] = input_kp; p.out[1] = input_conf; p.out[2] = target_kp; p.out[3] = target_conf;
   p.out[4] = left_kp; p.out[5] = left_conf;
   p.n_frames_out = n_frames_out; p.input_bf16 = nullptr;

@@ -56,9 +56,9 @@ class PreprocessRightHand:
         out["right_hand_kp"], out["right_hand_conf"] = out["target_kp"], out["target_conf"]
         return out
 
-    def __call__(self, pose25, hand_left, hand_right, win_start, T):
+    def __call__(self, pose25, hand_left, hand_right, win_start, T, out=None):
         """pose25 (F,25,3), hand_left/right (F,21,3) fp32 CUDA tensors (OpenPose [x,y,c]); win_start (W,)
-        int64; returns the stacked item dict: input_kp (W,T,12,2), input_conf (W,T,12), target_kp
+        int64; `out` = the dict returned by an earlier call with the same (W, T) to reuse its buffers; returns the stacked item dict: input_kp (W,T,12,2), input_conf (W,T,12), target_kp
         (W,T,21,2), target_conf (W,T,21), left_hand_*, n_frames (W,) int64 (device)."""
         _lib.require_device(pose25, "pose25")
         _lib.require_sm100(pose25.device)
@@ -69,8 +69,11 @@ class PreprocessRightHand:
         pose25, hand_left, hand_right = (_dev_f32(a, dev) for a in (pose25, hand_left, hand_right))
         ws = torch.as_tensor(win_start).to(device=dev, dtype=torch.int64).contiguous()
         W = ws.numel()
-        out = self._outputs(W, T, 12, dev)
-        bf = torch.empty((W, T, 24), dtype=torch.bfloat16, device=dev) if self.emit_bf16 else None
+        if out is None:
+            out = self._outputs(W, T, 12, dev)
+            bf = torch.empty((W, T, 24), dtype=torch.bfloat16, device=dev) if self.emit_bf16 else None
+        else:      # caller-owned output dict of a previous call with the same (W, T): steady-state loops, CUDA graphs
+            bf = out["input_kp_bf16"].view(W, T, 24) if self.emit_bf16 else None
         lib = _lib.load()
         _lib.check(lib.b2h_preprocess(_lib.ptr(pose25), _lib.ptr(hand_left), _lib.ptr(hand_right), F, _lib.ptr(ws), W, T,
                                       self.pad_mode, self.factor, int(self.dif_encoding), int(self.normalize),

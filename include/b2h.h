@@ -81,6 +81,11 @@ int b2h_preprocess(const float* pose25, const float* hand_left, const float* han
                    int normalize, float* input_kp, float* input_conf, float* target_kp, float* target_conf,
                    float* left_kp, float* left_conf, int64_t* n_frames_out, void* input_kp_bf16, void* stream);
 
+/* Test aid for the kernel's division: counts, over ALL 2^32 float bit patterns x, the cases where the
+ * reciprocal+FMA division used for `factor` differs from IEEE div.rn(x, factor) (must be 0; mismatches_dev is a
+ * zero-initialised device uint64). */
+int b2h_verify_fastdiv(float factor, unsigned long long* mismatches_dev, void* stream);
+
 /* Same for the packed H5 row format of TextPoseH5Dataset.array2item
  * (dataloaders/text_pose_dataset.py:587-612): rows (F,150) = [x0..x49 | y0..y49 | c0..c49],
  * body = columns 0..7 (8 keypoints), left hand 8..28, right hand 29..49.  Outputs (W,T,8,2) (W,T,8) ... */

@@ -104,3 +104,14 @@ def test_full_size_stream_properties():
     want = oracle.preprocess_windows(pose[pick], lh[pick], rh[pick], np.array([0]), 2000)
     assert np.array_equal(frames["input_kp"][0][torch.from_numpy(pick).to(dev)].cpu().numpy(), want["input_kp"][0])
     assert np.array_equal(frames["target_kp"][0][torch.from_numpy(pick).to(dev)].cpu().numpy(), want["target_kp"][0])
+
+
+def test_fast_division_is_exact_for_all_floats():
+    """The kernel divides by 1280 with reciprocal + two FMAs instead of the generic div.rn routine; the identity is
+    checked against IEEE div.rn for every one of the 2^32 float bit patterns (NaNs compare equal)."""
+    from hand_pose_sl_b200 import _lib
+    lib = _lib.load()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda:0")
+    _lib.check(lib.b2h_verify_fastdiv(1280.0, _lib.ptr(bad), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
