@@ -16,10 +16,12 @@
 // 4 slots (162 float4) go back with coalesced 128-bit stores.  Padded / unaligned groups take a scalar
 // path inside the same kernel (warp-uniform branch).  IEEE sub.rn then div.rn: no reciprocal, no FMA.
 #include "b2h_common.cuh"
+#define B2H_TC_NO_STATUS
+#include "b2h_tc.cuh"   // mbarrier + 1-D TMA bulk copy helpers
 
 namespace b2h {
 
-constexpr int kWarpsPerBlock = 8;
+constexpr int kWarpsPerBlock = 4;
 
 template <int FMT> struct Fmt;
 // FMT 0: OpenPose [x,y,c] rows: pose25 (75) | hand_left (63) | hand_right (63)
@@ -101,13 +103,12 @@ __device__ __forceinline__ float out_elem(const float* st, int a, int i, int r, 
 // identity for c = 1280 over ALL 2^32 float bit patterns on the device (b2h_verify_fastdiv).
 __device__ __forceinline__ float div_exact(float x, float c, float rc) {
   const float ax = fabsf(x);
-  if (ax == 0.0f) return x;                 // (+-0)/c = +-0 for the positive factor (the FMA chain would lose -0)
-  if (ax < 1e30f && ax > 1e-30f) {
-    const float q = __fmul_rn(x, rc);
-    const float r = __fmaf_rn(-q, c, x);
-    return __fmaf_rn(r, rc, q);
-  }
-  return __fdiv_rn(x, c);
+  const float q = __fmul_rn(x, rc);
+  const float r = __fmaf_rn(-q, c, x);
+  float res = __fmaf_rn(r, rc, q);
+  res = (ax == 0.0f) ? x : res;             // (+-0)/c = +-0 for the positive factor (the FMA chain would lose -0)
+  if (!(ax < 1e30f) || (ax != 0.0f && !(ax > 1e-30f))) res = __fdiv_rn(x, c);   // never taken on keypoint data
+  return res;
 }
 
 __global__ void verify_fastdiv_kernel(float c, float rc, unsigned long long* mismatches) {
@@ -141,20 +142,20 @@ __device__ __forceinline__ uint32_t table_entry(int a, int i, int r, const PreAr
     case 4: src = (uint32_t)(&F::lh_ref(z, i, j, d) - z); break;
     default: src = (uint32_t)(&F::lh_ref(z, i, r, 2) - z); break;
   }
-  return src | (ref << 16);
+  return (src * 4u) | ((ref * 4u) << 16);      // byte offsets into the warp's staged tile
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) preprocess_kernel(PreArgs p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) preprocess_kernel(PreArgs p) {
   using F = Fmt<FMT>;
   constexpr int kMaxQ = F::kBody * 3 + 126;             // float4 per 4-slot group over all six arrays
   constexpr int kZero = F::kStage;                      // 4 zero floats behind every warp's staged tile
-  __shared__ __align__(16) float stage_all[kWarpsPerBlock][F::kStage + 4];
+  __shared__ __align__(16) float stage_all[kWarpsPerBlock][2][F::kStage + 4];   // double-buffered per warp
+  __shared__ __align__(8) uint64_t sbar[kWarpsPerBlock][2];
   __shared__ __align__(16) uint32_t tab[kMaxQ * 4];
   __shared__ uint16_t qinfo[kMaxQ];
   __shared__ int s_nq, s_nq_div;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  float* st = stage_all[wib];
   const int64_t S = (int64_t)p.n_win * p.T;
   const int64_t n_groups = (S + 3) >> 2;
   const int n_out[6] = {F::kBody * 2, F::kBody, 42, 21, 42, 21};
@@ -188,77 +189,71 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) preprocess_kernel(PreArgs
         tab[q * 4 + e] = table_entry<FMT>(a, i, r, p, kZero);
       }
     }
-    if (lane < 4) st[kZero + lane] = 0.0f;
+    if (lane < 8) stage_all[wib][lane >> 2][kZero + (lane & 3)] = 0.0f;
+    if (lane == 0) { tc::mbar_init(&sbar[wib][0], 1); tc::mbar_init(&sbar[wib][1], 1); tc::fence_barrier_init(); }
   }
   __syncthreads();
   const int nq = s_nq, nq_div = s_nq_div;
   const float factor = p.factor, rfactor = p.rfactor;
   const bool fastdiv = p.fastdiv != 0;
   const bool small = S < (int64_t)0x7fffffff;
+  // Every lane owns the same output float4 slots (q = lane + 32*round) in every group, so its destination array
+  // and row length are loop invariants kept in registers.
+  constexpr int kRounds = (kMaxQ + 31) / 32;
+  float* obase[kRounds];
+  int ostride[kRounds];
+#pragma unroll
+  for (int r = 0; r < kRounds; ++r) {
+    const int q = lane + 32 * r;
+    obase[r] = nullptr; ostride[r] = 0;
+    if (q < nq) {
+      const int qi = qinfo[q];
+      const int a = qi >> 8;
+      obase[r] = p.out[a] + (qi & 255) * 4;
+      ostride[r] = n_out[a];
+    }
+  }
 
-  for (int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + wib; g < n_groups; g += (int64_t)gridDim.x * kWarpsPerBlock) {
-    const int64_t s0 = g << 2;
-    // ---- window index math (bit-exact integer work): slot s -> (window, t) -> source frame ----
-    int64_t w0; int t0;
-    if (small) { const int si = (int)s0; const int wi = si / p.T; w0 = wi; t0 = si - wi * p.T; }
-    else { w0 = s0 / p.T; t0 = (int)(s0 - w0 * p.T); }
+  // Stage the 4 source frames of group gg into buffer b of this warp.  Aligned groups are moved by the TMA engine
+  // (3 bulk copies, completion on the buffer's mbarrier) one group AHEAD of the compute; padded / unaligned groups
+  // are filled by the lanes.  Either way exactly one arrival completes the buffer's phase.
+  auto issue = [&](int64_t gg, int b) {
+    float* st = stage_all[wib][b];
+    const int64_t s0 = gg << 2;
+    // window index math (bit-exact integer work): slot s -> (window, t) -> source frame
+    int64_t w; int t;
+    if (small) { const int si = (int)s0; const int wi = si / p.T; w = wi; t = si - wi * p.T; }
+    else { w = s0 / p.T; t = (int)(s0 - w * p.T); }
     int64_t srcf[4];
     bool consecutive = true;
-    {
-      int64_t w = w0; int t = t0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (s0 + i < S) {
-          const int64_t start = p.win_start[w];
-          int64_t f = start + t;                        // crop [start, start+T)   text_pose_dataset.py:66-68
-          if (f >= p.n_frames || f < 0)                 // past the clip end -> pad rule
-            f = (p.pad_mode == B2H_PAD_REPEAT_FIRST && start >= 0 && start < p.n_frames) ? start : -1;  // :512-518 / :616-622
-          srcf[i] = f;
-          if (t == 0 && lane == 0 && p.n_frames_out) {
-            const int64_t rem = p.n_frames - start;
-            p.n_frames_out[w] = rem < 0 ? 0 : (rem < p.T ? rem : (int64_t)p.T);   // :447
-          }
-        } else {
-          srcf[i] = -1;
+    for (int i = 0; i < 4; ++i) {
+      if (s0 + i < S) {
+        const int64_t start = p.win_start[w];
+        int64_t f = start + t;                        // crop [start, start+T)   text_pose_dataset.py:66-68
+        if (f >= p.n_frames || f < 0)                 // past the clip end -> pad rule
+          f = (p.pad_mode == B2H_PAD_REPEAT_FIRST && start >= 0 && start < p.n_frames) ? start : -1;  // :512-518 / :616-622
+        srcf[i] = f;
+        if (t == 0 && lane == 0 && p.n_frames_out) {
+          const int64_t rem = p.n_frames - start;
+          p.n_frames_out[w] = rem < 0 ? 0 : (rem < p.T ? rem : (int64_t)p.T);   // :447
         }
-        if (i > 0 && srcf[i] != srcf[0] + i) consecutive = false;
-        if (++t == p.T) { t = 0; ++w; }
-      }
-    }
-    const bool full = (s0 + 3 < S);
-    const bool fast = p.aligned && consecutive && srcf[0] >= 0 && (srcf[0] & 3) == 0 && full;
-    __syncwarp();
-    // ---- stage 4 source frames in shared memory ----
-    if (fast) {
-      if (FMT == 0) {
-        // 75 + 63 + 63 = 201 float4: all seven loads of a lane are issued before the first store
-        const float4* g0 = reinterpret_cast<const float4*>(p.src[0] + srcf[0] * 75);
-        const float4* g1 = reinterpret_cast<const float4*>(p.src[1] + srcf[0] * 63);
-        const float4* g2 = reinterpret_cast<const float4*>(p.src[2] + srcf[0] * 63);
-        float4 v[7];
-        v[0] = __ldcs(g0 + lane); v[1] = __ldcs(g0 + 32 + lane);
-        if (lane < 11) v[2] = __ldcs(g0 + 64 + lane);
-        v[3] = __ldcs(g1 + lane);
-        if (lane < 31) v[4] = __ldcs(g1 + 32 + lane);
-        v[5] = __ldcs(g2 + lane);
-        if (lane < 31) v[6] = __ldcs(g2 + 32 + lane);
-        float4* s4 = reinterpret_cast<float4*>(st);
-        s4[lane] = v[0]; s4[32 + lane] = v[1];
-        if (lane < 11) s4[64 + lane] = v[2];
-        s4[75 + lane] = v[3];
-        if (lane < 31) s4[75 + 32 + lane] = v[4];
-        s4[138 + lane] = v[5];
-        if (lane < 31) s4[138 + 32 + lane] = v[6];
       } else {
-        const float4* g0 = reinterpret_cast<const float4*>(p.src[0] + srcf[0] * 150);
-        float4 v[5];
+        srcf[i] = -1;
+      }
+      if (i > 0 && srcf[i] != srcf[0] + i) consecutive = false;
+      if (++t == p.T) { t = 0; ++w; }
+    }
+    const bool fast = p.aligned && consecutive && srcf[0] >= 0 && (srcf[0] & 3) == 0 && (s0 + 3 < S);
+    if (fast) {
+      if (lane == 0) {
+        uint32_t bytes = 0;
 #pragma unroll
-        for (int r = 0; r < 5; ++r)
-          if (r * 32 + lane < 150) v[r] = __ldcs(g0 + r * 32 + lane);
-        float4* s4 = reinterpret_cast<float4*>(st);
+        for (int a = 0; a < F::kSrc; ++a) bytes += 16u * F::src_len(a);
+        tc::mbar_arrive_expect_tx(&sbar[wib][b], bytes);
 #pragma unroll
-        for (int r = 0; r < 5; ++r)
-          if (r * 32 + lane < 150) s4[r * 32 + lane] = v[r];
+        for (int a = 0; a < F::kSrc; ++a)
+          tc::bulk_g2s(st + F::src_off(a), p.src[a] + srcf[0] * F::src_len(a), 16u * F::src_len(a), &sbar[wib][b]);
       }
     } else {
 #pragma unroll
@@ -275,28 +270,51 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) preprocess_kernel(PreArgs
           }
         }
       }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&sbar[wib][b]);
     }
-    __syncwarp();
+  };
+
+  const int64_t gstride = (int64_t)gridDim.x * kWarpsPerBlock;
+  int64_t g = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+  if (g < n_groups) issue(g, 0);
+  for (int it = 0; g < n_groups; g += gstride, ++it) {
+    const int b = it & 1;
+    __syncwarp();                                   // every lane is done reading buffer b^1 (previous group)
+    if (g + gstride < n_groups) issue(g + gstride, b ^ 1);
+    {                                               // wait for this group's frames
+      const uint32_t parity = (uint32_t)(it >> 1) & 1u;
+      const long long t0 = clock64();
+      while (!tc::mbar_try_wait(&sbar[wib][b], parity))
+        if (clock64() - t0 > 4000000000LL) break;   // never spin forever (a wrong answer is caught by the tests)
+    }
+    const float* st = stage_all[wib][b];
+    const char* stb = reinterpret_cast<const char*>(st);
+    const int64_t s0 = g << 2;
+    const bool full = (s0 + 3 < S);
     // ---- the six output rows of the 4 slots ----
     if (full) {
-      for (int q = lane; q < nq; q += 32) {
-        const uint4 e4 = *reinterpret_cast<const uint4*>(tab + q * 4);
-        const uint32_t en[4] = {e4.x, e4.y, e4.z, e4.w};
-        float v[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = __fsub_rn(st[en[e] & 0xFFFFu], st[en[e] >> 16]);   // utils.py:200 / :209 (x - 0 = x)
-        if (q < nq_div) {                                                                  // utils.py:186-188
-          if (fastdiv) {
+      for (int r = 0; r < kRounds; ++r) {
+        const int q = lane + 32 * r;
+        if (q < nq) {
+          const uint4 e4 = *reinterpret_cast<const uint4*>(tab + q * 4);
+          const uint32_t en[4] = {e4.x, e4.y, e4.z, e4.w};
+          float v[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = div_exact(v[e], factor, rfactor);
-          } else {
+          for (int e = 0; e < 4; ++e)   // utils.py:200 / :209 (x - 0 = x when there is no reference)
+            v[e] = __fsub_rn(*reinterpret_cast<const float*>(stb + (en[e] & 0xFFFFu)), *reinterpret_cast<const float*>(stb + (en[e] >> 16)));
+          if (q < nq_div) {                                                                  // utils.py:186-188
+            if (fastdiv) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = __fdiv_rn(v[e], factor);
+              for (int e = 0; e < 4; ++e) v[e] = div_exact(v[e], factor, rfactor);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = __fdiv_rn(v[e], factor);
+            }
           }
+          __stcs(reinterpret_cast<float4*>(obase[r] + s0 * ostride[r]), make_float4(v[0], v[1], v[2], v[3]));
         }
-        const int qi = qinfo[q];
-        const int a = qi >> 8, ql = qi & 255;
-        __stcs(reinterpret_cast<float4*>(p.out[a] + s0 * n_out[a]) + ql, make_float4(v[0], v[1], v[2], v[3]));
       }
       if (p.input_bf16) {  // bf16 copy of input_kp for the tensor-core net (no second pass over HBM)
         const int n = F::kBody * 2;
@@ -329,7 +347,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) preprocess_kernel(PreArgs
         }
       }
     }
-    __syncwarp();
   }
 }
 
@@ -339,7 +356,7 @@ static int launch_pre(PreArgs& p, cudaStream_t stream) {
   int64_t S = (int64_t)p.n_win * p.T;
   int64_t groups = (S + 3) / 4;
   int64_t blocks = (groups + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  int64_t cap = (int64_t)num_sms() * 8;            // 8 resident CTAs/SM, grid-stride beyond that
+  int64_t cap = (int64_t)num_sms() * 7;            // 7 resident CTAs/SM (shared memory), grid-stride beyond that
   if (blocks > cap) blocks = cap;
   preprocess_kernel<FMT><<<(unsigned)blocks, kWarpsPerBlock * 32, 0, stream>>>(p);
   count_launch();

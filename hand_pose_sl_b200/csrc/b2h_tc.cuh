@@ -44,6 +44,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                : "memory");
 }
 
+#ifndef B2H_TC_NO_STATUS
 // Device-side status word: a wait that exceeds its budget records the site and returns so a
 // descriptor / protocol bug ends as a wrong answer + error code, never as a hung GPU.
 __device__ int g_tc_status = 0;
@@ -58,6 +59,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int si
   }
   return true;
 }
+#endif  // B2H_TC_NO_STATUS
 
 // ---- proxies / fences -------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
