@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
     ap.add_argument("--skip-extras", action="store_true", help="only the headline train-step number")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="multi-GPU gradient exchange")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -154,6 +155,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("B2H_NCCL_DEBUG", "WARN")    # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()
     train_prec = "bf16" if args.precision == "auto" else args.precision
@@ -164,7 +166,7 @@ def main():
     model = b2h.ConvModel(C, "ReLU", False, precision=train_prec).to(dev)
     opt = b2h.FusedAdam(model.parameters(), lr=LR)
     if world > 1:
-        runner = DataParallelTrainer(model, opt, B_TRAIN, T, "L1", n_slots=N_SLOTS)
+        runner = DataParallelTrainer(model, opt, B_TRAIN, T, "L1", n_slots=N_SLOTS, exchange=args.exchange)
     else:
         runner = TrainStepRunner(model, opt, B_TRAIN, T, "L1", n_slots=N_SLOTS)
     host_batches = []
@@ -213,7 +215,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
-    launches_per_graph_step = 2 if world == 1 else 3          # train+adam | train+reduce+adam (the all-reduce is NCCL's)
+    launches_per_graph_step = 2 if world == 1 else 3          # train+adam | train+reduce+(adam | fused exchange+adam)
     gpu_launches = (_lib.launch_count() - launches0) if not graphed else args.steps // chunk * chunk * launches_per_graph_step + \
         (_lib.launch_count() - launches0)
     value = args.steps * B_TRAIN * T * world / (ms * 1e-3)
@@ -251,6 +253,7 @@ def main():
             "config": {"workload": f"train step (fwd+mask+L1+bwd+Adam), batch {B_TRAIN}x{T} frames per GPU, C={C} (BASELINE config 3/4)",
                        "global_batch": B_TRAIN * world, "frames_per_window": T, "conv_channels": C,
                        "parallelism": f"dp{world}", "cuda_graph": graphed,
+                       "grad_exchange": (getattr(runner, "exchange", None) if world > 1 else None),
                        "l2": f"{N_SLOTS} resident batches rotated ({N_SLOTS * (h2d) / 1e6:.0f} MB inputs + "
                              f"{_lib.workspace_bytes(B_TRAIN, T, 24, C, 0, _lib.PRECISIONS[train_prec]) / 1e6:.0f} MB gradient partials) > 126 MB L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "final_loss": final_loss}
@@ -356,8 +359,13 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Tearing the NCCL communicator down while a captured CUDA graph still holds its kernels hangs in
+        # destroy_process_group (seen on B200, torch 2.11 / NCCL 2.28): synchronise, then leave without the teardown.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -131,7 +131,7 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
                         const int32_t* lengths, const float* params, const void* packed, float* pred_out, int B, int T,
                         int n_in, int C, int pos_emb, int loss_kind, int precision, int mode, void* workspace,
                         int64_t workspace_bytes, cudaStream_t stream, Geo& g, int& nparts, float*& partials,
-                        float*& loss_partials, const char* who, long long* step_dev = nullptr) {
+                        float*& loss_partials, const char* who, long long* step_dev = nullptr, long long* epoch_dev = nullptr) {
   if (!x || !params || !packed || !workspace) { set_error("%s: null pointer", who); return B2H_EINVAL; }
   if (x_dtype != B2H_DT_F32 && x_dtype != B2H_DT_BF16) { set_error("%s: bad x_dtype %d", who, x_dtype); return B2H_EINVAL; }
   if (!geo_ok(n_in, C, pos_emb, who)) return B2H_ESHAPE;
@@ -160,6 +160,7 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
   a.packed = reinterpret_cast<const char*>(packed); a.y = pred_out; a.partials = partials; a.loss_partials = loss_partials;
   a.B = B; a.T = T; a.loss_kind = loss_kind; a.apply_mask = 1; a.mode = mode; a.out_scale = 1.0f; a.geo = g;
   a.step_dev = step_dev;
+  a.epoch_dev = epoch_dev;
   if (use_tc_train(g, T, precision)) return launch_tc_tile_train(a, stream);
   return launch_fp32(a, true, stream, nparts);
 }
@@ -177,6 +178,38 @@ extern "C" int b2h_train_forward_backward(const void* x, int x_dtype, const floa
   if (rc || !grads_out) return rc;   // grads_out == NULL: only the fused kernel runs, partials stay in the workspace
   return launch_reduce(partials, nparts, use_tc_train(g, T, precision) ? 1 : 0, g, grads_out, loss_partials, loss_out, (cudaStream_t)stream);
 }
+
+extern "C" int b2h_train_forward_backward_dp(const void* x, int x_dtype, const float* target, const float* conf,
+                                             const int32_t* lengths, const float* params, const void* packed,
+                                             float* sym_grads, float* loss_out, int B, int T, int n_in, int C, int pos_emb,
+                                             int loss_kind, int precision, int64_t* step_dev, int64_t* epoch_dev,
+                                             void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!sym_grads || !loss_out || !step_dev || !epoch_dev) { set_error("b2h_train_forward_backward_dp: null pointer"); return B2H_EINVAL; }
+  Geo g; int nparts; float *partials, *loss_partials;
+  int rc = train_common(x, x_dtype, target, conf, nullptr, lengths, params, packed, nullptr, B, T, n_in, C, pos_emb,
+                        loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
+                        loss_partials, "b2h_train_forward_backward_dp", reinterpret_cast<long long*>(step_dev),
+                        reinterpret_cast<long long*>(epoch_dev));
+  if (rc) return rc;
+  return launch_reduce(partials, nparts, use_tc_train(g, T, precision) ? 1 : 0, g, sym_grads, loss_partials, loss_out,
+                       (cudaStream_t)stream, reinterpret_cast<const long long*>(epoch_dev));
+}
+
+extern "C" int b2h_adam_step_dp(float* params, const void* peer_bufs_dev, int rank, int world, float* exp_avg, float* exp_avg_sq,
+                                int64_t n, double lr, double beta1, double beta2, double eps, const int64_t* step_dev,
+                                const int64_t* epoch_dev, float grad_scale, void* packed, int n_in, int C, int pos_emb,
+                                void* stream) {
+  if (!params || !peer_bufs_dev || !exp_avg || !exp_avg_sq || !step_dev || !epoch_dev) { set_error("b2h_adam_step_dp: null pointer"); return B2H_EINVAL; }
+  if (world < 1 || world > 32 || rank < 0 || rank >= world) { set_error("b2h_adam_step_dp: bad rank/world"); return B2H_EINVAL; }
+  if (!geo_ok(n_in, C, pos_emb, "b2h_adam_step_dp")) return B2H_ESHAPE;
+  Geo g = make_geo(n_in, C, pos_emb);
+  if (g.P != n) { set_error("b2h_adam_step_dp: n=%lld does not match geometry (%d)", (long long)n, g.P); return B2H_ESHAPE; }
+  return launch_adam_dp(params, reinterpret_cast<const float* const*>(peer_bufs_dev), rank, world, exp_avg, exp_avg_sq, n, lr, beta1,
+                        beta2, eps, reinterpret_cast<const long long*>(step_dev), reinterpret_cast<const long long*>(epoch_dev),
+                        grad_scale, packed, g, (cudaStream_t)stream);
+}
+
+extern "C" int b2h_dp_status(void) { return dp_status_and_clear(); }
 
 extern "C" int b2h_conv_backward(const void* x, int x_dtype, const float* d_y, const float* params, const void* packed,
                                  float* grads_out, int B, int T, int n_in, int C, int pos_emb, int precision,

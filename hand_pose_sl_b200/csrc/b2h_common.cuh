@@ -123,6 +123,7 @@ struct Fp32Args {
   float* partials;          // [grid][P]
   float* loss_partials;     // [grid]
   long long* step_dev;      // nullable: device step counter, incremented by block 0 (read by the Adam kernel)
+  long long* epoch_dev;     // nullable: data-parallel exchange epoch, incremented the same way (never rewound)
   int B, T, loss_kind, apply_mask, mode;   // mode 0 = forward, 1 = train (loss inside), 2 = backward of given d_y
   float out_scale;
   Geo geo;
@@ -155,7 +156,11 @@ void set_debug_timing(long long* p);
 int launch_tc_bench(long long* out, int M, int N, int reps, int nacc, int mn_major, cudaStream_t stream);
 int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t stream);
 int launch_reduce(const float* partials, int nparts, int gp_layout, const Geo& g, float* grads, const float* loss_partials,
-                  float* loss_out, cudaStream_t stream);
+                  float* loss_out, cudaStream_t stream, const long long* epoch_dev = nullptr);
+int launch_adam_dp(float* params, const float* const* peer_bufs, int rank, int world, float* m, float* v, int64_t n, double lr,
+                   double beta1, double beta2, double eps, const long long* step_dev, const long long* epoch_dev, float grad_scale,
+                   void* packed, const Geo& g, cudaStream_t stream);
+int dp_status_and_clear();
 int launch_adam(float* params, const float* grads, int nparts, int gp_layout, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                 double eps, int64_t step, const long long* step_dev, float grad_scale, void* packed, const Geo& g,
                 const float* loss_partials, float* loss_out, cudaStream_t stream);

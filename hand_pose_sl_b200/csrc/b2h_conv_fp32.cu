@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kThreads) conv_fp32_kernel(Fp32Args p) {
     bias[l] = p.params + g.b_off[l];
   }
   if (TRAIN && p.step_dev && blockIdx.x == 0 && threadIdx.x == 0) *p.step_dev += 1;
+  if (TRAIN && p.epoch_dev && blockIdx.x == 0 && threadIdx.x == 0) *p.epoch_dev += 1;
   float* part = TRAIN ? p.partials + (size_t)blockIdx.x * g.P : nullptr;
   float loss_acc = 0.0f;
   bool first = true;

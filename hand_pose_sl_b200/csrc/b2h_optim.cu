@@ -80,8 +80,9 @@ __device__ __forceinline__ void loss_partial_sum(const float* __restrict__ loss_
 // grads[i] = sum_c partials[c][slot(i)];  loss = sum_c loss_partials[c]
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int nparts, int gp_layout, Geo g,
                                                               float* __restrict__ grads, const float* __restrict__ loss_partials,
-                                                              float* __restrict__ loss_out) {
+                                                              float* __restrict__ loss_out, const long long* __restrict__ epoch_dev) {
   __shared__ float red[8][32];
+  if (epoch_dev) grads += (size_t)(*epoch_dev & 1) * g.P;      // data parallel: double-buffered exchange slot
   const int nj = gp_layout ? gp_total(g) : g.P;
   const int j = blockIdx.x * 32 + (threadIdx.x & 31);
   const float s = block_partial_sum(partials, nparts, (size_t)nj, j, nj, red);
@@ -140,6 +141,91 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
     }
   }
   loss_partial_sum(a.loss_partials, a.nparts, a.loss_out);
+}
+
+// ---- data parallel: gradient exchange over peer (NVLink) memory fused with Adam -------------------------------
+// Every rank owns a symmetric buffer  [2][P] fp32 gradients (double-buffered by epoch parity) + [world] uint64 flags.
+// Step protocol (one kernel per rank, all ranks run it concurrently on their own GPU):
+//   1. block 0 publishes "my gradients of epoch e are complete" by storing e into flag[rank] of every peer
+//      (the reduce kernel that wrote them is the previous kernel on the stream; __threadfence_system orders it);
+//   2. every block waits until all world flags in the LOCAL buffer have reached e (acquire loads, bounded spin);
+//   3. every thread sums its gradient element over the peers' buffers in rank order (identical arithmetic on
+//      every rank -> replicas stay bit-identical) and applies Adam + weight re-pack.
+// Re-use safety: a rank can be at most one epoch ahead of a peer (it needs the peer's flag for e+1 to pass 2.),
+// and epoch e+1 uses the other half of the buffer, so nobody overwrites data that is still being read.
+__device__ int g_dp_status = 0;
+
+struct AdamDpArgs {
+  AdamArgs a;
+  const float* const* peer_bufs;   // device array [world] of peer buffer base pointers (index = rank)
+  const long long* epoch_dev;
+  int rank, world;
+};
+
+__global__ void __launch_bounds__(256) adam_dp_kernel(AdamDpArgs d) {
+  AdamArgs& a = d.a;
+  __shared__ float s_step_size, s_inv_bc2_sqrt;
+  const long long epoch = *d.epoch_dev;
+  const size_t P = (size_t)a.n;
+  const size_t flag_off = 2 * P;                       // in floats; flags are 8-byte aligned (2P is even)
+  if (threadIdx.x == 0) {
+    const double t = (double)*a.step_dev;
+    s_step_size = (float)(a.lr_d / (1.0 - pow(a.beta1_d, t)));
+    s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(a.beta2_d, t)));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < d.world) {
+    __threadfence_system();
+    volatile long long* f = reinterpret_cast<volatile long long*>(const_cast<float*>(d.peer_bufs[threadIdx.x]) + flag_off) + d.rank;
+    *f = epoch;
+    __threadfence_system();
+  }
+  if (threadIdx.x < d.world) {
+    const volatile long long* f = reinterpret_cast<const volatile long long*>(d.peer_bufs[d.rank] + flag_off) + threadIdx.x;
+    const long long t0 = clock64();
+    while (*f < epoch) {
+      if (clock64() - t0 > 6000000000LL) { atomicExch(&g_dp_status, 1); break; }   // ~3 s: never hang the box
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < a.n) {
+    const size_t off = (size_t)(epoch & 1) * P + (size_t)i;
+    float gr = 0.f;
+    for (int r = 0; r < d.world; ++r) gr += __ldcv(d.peer_bufs[r] + off);
+    gr *= a.grad_scale;
+    float m = a.m[i], v = a.v[i], p = a.params[i];
+    m = fmaf(gr - m, a.one_minus_b1, m);
+    v = fmaf(a.one_minus_b2 * gr, gr, v * a.beta2);
+    const float denom = sqrtf(v) * s_inv_bc2_sqrt + a.eps;
+    p = p - s_step_size * (m / denom);
+    a.m[i] = m; a.v[i] = v; a.params[i] = p;
+    if (a.packed) scatter_packed(a.g, a.packed, (int)i, p);
+  }
+}
+
+int launch_adam_dp(float* params, const float* const* peer_bufs, int rank, int world, float* m, float* v, int64_t n, double lr,
+                   double beta1, double beta2, double eps, const long long* step_dev, const long long* epoch_dev, float grad_scale,
+                   void* packed, const Geo& g, cudaStream_t stream) {
+  AdamDpArgs d{};
+  AdamArgs& a = d.a;
+  a.params = params; a.grads = nullptr; a.nparts = 1; a.gp_layout = 0; a.n = n; a.m = m; a.v = v;
+  a.beta1 = (float)beta1; a.beta2 = (float)beta2;
+  a.one_minus_b1 = (float)(1.0 - beta1); a.one_minus_b2 = (float)(1.0 - beta2);
+  a.eps = (float)eps; a.grad_scale = grad_scale;
+  a.packed = reinterpret_cast<char*>(packed); a.g = g;
+  a.lr_d = lr; a.beta1_d = beta1; a.beta2_d = beta2; a.step_dev = step_dev;
+  d.peer_bufs = peer_bufs; d.epoch_dev = epoch_dev; d.rank = rank; d.world = world;
+  adam_dp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d);
+  count_launch();
+  return check_launch("adam_dp_kernel");
+}
+
+int dp_status_and_clear() {
+  int v = 0, z = 0;
+  cudaMemcpyFromSymbol(&v, g_dp_status, sizeof(int));
+  if (v) cudaMemcpyToSymbol(g_dp_status, &z, sizeof(int));
+  return v;
 }
 
 __global__ void mask_output_kernel(float* __restrict__ y, const int32_t* __restrict__ lengths, int B, int T, int row) {
@@ -209,9 +295,9 @@ int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t st
 }
 
 int launch_reduce(const float* partials, int nparts, int gp_layout, const Geo& g, float* grads, const float* loss_partials,
-                  float* loss_out, cudaStream_t stream) {
+                  float* loss_out, cudaStream_t stream, const long long* epoch_dev) {
   const int nj = gp_layout ? gp_total(g) : g.P;
-  reduce_partials_kernel<<<(nj + 31) / 32, 256, 0, stream>>>(partials, nparts, gp_layout, g, grads, loss_partials, loss_out);
+  reduce_partials_kernel<<<(nj + 31) / 32, 256, 0, stream>>>(partials, nparts, gp_layout, g, grads, loss_partials, loss_out, epoch_dev);
   count_launch();
   return check_launch("reduce_partials_kernel");
 }

@@ -41,6 +41,7 @@ struct TcTileArgs {
   float* partials;        // [grid][GP]  (gradient-partial layout, b2h_common.cuh gp_*)
   float* loss_partials;   // [grid]
   long long* step_dev;
+  long long* epoch_dev;
   long long* dbg;         // nullable: CTA 0 / thread 0 writes clock64() phase stamps here (b2h_debug_timing)
   int B, T, loss_kind, apply_mask, mode;   // mode 0 = forward only, 1 = train (loss inside), 2 = backward of given d_y
   float out_scale;
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
     }
   }
   if (TRAIN && p.step_dev && blockIdx.x == 0 && tid == 0) *p.step_dev += 1;
+  if (TRAIN && p.epoch_dev && blockIdx.x == 0 && tid == 0) *p.epoch_dev += 1;
   {  // zero every activation / gradient buffer once: pad rows and pad channels stay zero
     const int act_bytes = L.ys;
     uint4* z = reinterpret_cast<uint4*>(smem);
@@ -598,7 +600,7 @@ int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream) {
   TcTileArgs p{};
   p.x = a.x; p.x_dtype = a.x_dtype; p.target = a.target; p.conf = a.conf; p.d_y = a.d_y; p.lengths = a.lengths;
   p.params = a.params; p.packed = a.packed; p.y = a.y; p.partials = a.partials; p.loss_partials = a.loss_partials;
-  p.step_dev = a.step_dev; p.B = a.B; p.T = a.T; p.loss_kind = a.loss_kind; p.apply_mask = 1; p.mode = a.mode;
+  p.step_dev = a.step_dev; p.epoch_dev = a.epoch_dev; p.B = a.B; p.T = a.T; p.loss_kind = a.loss_kind; p.apply_mask = 1; p.mode = a.mode;
   p.out_scale = 1.0f; p.geo = a.geo;
   p.dbg = g_dbg_timing;
   return launch_tc_tile(p, true, stream);

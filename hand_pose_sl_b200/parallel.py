@@ -61,13 +61,33 @@ def broadcast_parameters(model: ConvModel, src: int = 0, group=None):
         model.mark_packed_stale()
 
 
+def _symmetric_exchange_buffer(n_params: int, device, group):
+    """Peer-mapped buffer [2][P] fp32 gradients + [world] int64 flags on every rank (torch symmetric memory:
+    cuMem allocations mapped into every peer over NVLink).  Returns (local tensor, device array of peer base
+    pointers indexed by rank)."""
+    import torch.distributed._symmetric_memory as symm_mem
+    world = dist.get_world_size(group)
+    n = 2 * n_params + 2 * world + 8                     # flags are int64 = 2 floats each
+    buf = symm_mem.empty(n, dtype=torch.float32, device=device)
+    buf.zero_()
+    hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+    ptrs = [int(p) for p in hdl.buffer_ptrs]
+    if len(ptrs) != world or hdl.rank != dist.get_rank(group):
+        raise RuntimeError("symmetric memory rendezvous returned an unexpected peer table")
+    torch.cuda.synchronize(device)
+    dist.barrier(group)                                   # every rank's buffer is zeroed before anyone signals
+    return buf, hdl, torch.tensor(ptrs, dtype=torch.int64, device=device)
+
+
 class DataParallelTrainer:
-    """One process per GPU.  step() = [forward+mask+loss+backward kernel, partial-reduce kernel] ->
-    all-reduce(flat grads) -> [Adam + repack kernel with grad_scale = 1/W].  Static buffers; the
-    whole step can be captured in a CUDA graph (NCCL collectives are capturable)."""
+    """One process per GPU.  exchange="p2p" (default when symmetric memory is available): step() = [forward+mask+
+    loss+backward kernel, partial-reduce kernel -> peer-mapped buffer] -> [ONE kernel: flag exchange with all peers,
+    sum of the peers' gradients over NVLink, Adam + re-pack] -- the collective is fused with the optimiser, no NCCL
+    call on the step path.  exchange="nccl": ... -> dist.all_reduce(flat grads) -> Adam kernel (baseline).
+    Static buffers; the whole step can be captured in a CUDA graph either way."""
 
     def __init__(self, model: ConvModel, optimizer: FusedAdam, B: int, T: int, loss: str = "L1", group=None,
-                 n_slots: int = 1):
+                 n_slots: int = 1, exchange: str = "auto"):
         self.model, self.opt, self.B, self.T, self.loss_name, self.group = model, optimizer, B, T, loss, group
         self.kind = _lib.LOSSES[loss]
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -95,6 +115,21 @@ class DataParallelTrainer:
         self.lib = _lib.load()
         self.host_steps = int(self.state["step"])
         self.graph, self._graph_steps = None, 0
+        if exchange not in ("auto", "p2p", "nccl"):
+            raise ValueError("exchange must be 'auto', 'p2p' or 'nccl'")
+        self.exchange = "nccl"
+        self.sym = self.sym_hdl = self.peer_ptrs = None
+        if self.world > 1 and exchange in ("auto", "p2p"):
+            try:
+                self.sym, self.sym_hdl, self.peer_ptrs = _symmetric_exchange_buffer(flat.numel(), dev, group)
+                self.epoch_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
+                self.rank = dist.get_rank(group)
+                self.exchange = "p2p"
+            except Exception as e:  # noqa: BLE001  (no peer access / symmetric memory unavailable)
+                if exchange == "p2p":
+                    raise
+                import warnings
+                warnings.warn(f"symmetric-memory gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
 
     def load(self, batch, slot=0, non_blocking=True):
         self.x[slot].copy_(batch["input_kp"], non_blocking=non_blocking)
@@ -109,6 +144,19 @@ class DataParallelTrainer:
         b1, b2 = g["betas"]
         conf = None if self.conf is None else self.conf[slot]
         sp = _lib.stream_ptr(self.dev)
+        if self.exchange == "p2p":
+            _lib.check(self.lib.b2h_train_forward_backward_dp(
+                _lib.ptr(self.x[slot]), _lib.DT_F32, _lib.ptr(self.target[slot]), _lib.ptr(conf), _lib.ptr(self.lengths[slot]),
+                _lib.ptr(m._flat), _lib.ptr(self.packed), _lib.ptr(self.sym), _lib.ptr(self.loss[slot:slot + 1]),
+                self.B, self.T, n_in, C, pe, self.kind, _lib.PRECISIONS[m.precision], _lib.ptr(self.step_dev),
+                _lib.ptr(self.epoch_dev), _lib.ptr(self.ws), self.ws.numel(), sp))
+            _lib.check(self.lib.b2h_adam_step_dp(
+                _lib.ptr(m._flat), _lib.ptr(self.peer_ptrs), self.rank, self.world, _lib.ptr(self.state["m"]),
+                _lib.ptr(self.state["v"]), m._flat.numel(), float(g["lr"]), b1, b2, g["eps"], _lib.ptr(self.step_dev),
+                _lib.ptr(self.epoch_dev), grad_scale_for(self.loss_name, self.world), _lib.ptr(self.packed), n_in, C, pe, sp))
+            self.host_steps += 1
+            self.state["step"] = self.host_steps
+            return self.loss[slot]
         _lib.check(self.lib.b2h_train_forward_backward(
             _lib.ptr(self.x[slot]), _lib.DT_F32, _lib.ptr(self.target[slot]), _lib.ptr(conf), _lib.ptr(self.lengths[slot]),
             _lib.ptr(m._flat), _lib.ptr(self.packed), _lib.ptr(self.grads), _lib.ptr(self.loss[slot:slot + 1]), None,

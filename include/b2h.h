@@ -144,6 +144,25 @@ int b2h_adam_step(float* params, const float* grads, float* exp_avg, float* exp_
                   double beta1, double beta2, double eps, int64_t step, const int64_t* step_dev, float grad_scale,
                   void* packed, int n_in, int C, int pos_emb, void* stream);
 
+/* ---- data parallel over peer (NVLink / NVSwitch) memory -----------------------------------------------------
+ * The reference is single-process; training shards by batch with ONE gradient exchange per step.
+ * Every rank owns a symmetric buffer  [2][P] fp32 + [world] int64 flags  (zero-initialised, peer-mapped, e.g.
+ * torch.distributed._symmetric_memory).  b2h_train_forward_backward_dp = b2h_train_forward_backward whose reduced
+ * flat gradient lands in sym_grads[(epoch & 1) * P ...]; b2h_adam_step_dp = flag exchange with all peers, sum of the
+ * peers' gradients in rank order over NVLink and Adam + re-pack, in ONE kernel (no NCCL call on the step path).
+ * step_dev / epoch_dev: device int64 counters advanced by the train kernel (epoch_dev is never rewound).
+ * peer_bufs_dev: device array [world] of the peers' buffer base pointers, indexed by rank. */
+int b2h_train_forward_backward_dp(const void* x, int x_dtype, const float* target, const float* conf,
+                                  const int32_t* lengths, const float* params, const void* packed, float* sym_grads,
+                                  float* loss_out, int B, int T, int n_in, int C, int pos_emb, int loss_kind,
+                                  int precision, int64_t* step_dev, int64_t* epoch_dev, void* workspace,
+                                  int64_t workspace_bytes, void* stream);
+int b2h_adam_step_dp(float* params, const void* peer_bufs_dev, int rank, int world, float* exp_avg, float* exp_avg_sq,
+                     int64_t n, double lr, double beta1, double beta2, double eps, const int64_t* step_dev,
+                     const int64_t* epoch_dev, float grad_scale, void* packed, int n_in, int C, int pos_emb, void* stream);
+/* 0 = clean, 1 = a peer-flag wait gave up (bounded spin); reading clears it.  Synchronises the device. */
+int b2h_dp_status(void);
+
 /* Fast path = b2h_train_forward_backward + b2h_adam_step with the cross-CTA gradient reduction
  * fused into the Adam kernel (2 launches per step, zero host work).  step_dev (nullable): a device
  * int64 holding the number of steps taken so far; when given it is incremented on the device and
