@@ -151,6 +151,10 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: hand_pose_sl_b200 has no CPU path (use --impl reference for the CPU arm)")
+    # libraries (NCCL's version banner, ...) write to stdout; keep fd 1 clean for the ONE JSON line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -356,6 +360,13 @@ def main():
         # ---------------- CPU baseline (reference path on this box's host cores) ----------------
         line["cpu_baseline"], _, _ = cpu_reference_arm(200, 2, budget_s=15.0)
 
+    sys.stdout.flush()
+    try:                                   # NCCL's banner sits in the C stdio buffer: push it to the redirected fd first
+        import ctypes
+        ctypes.CDLL(None).fflush(None)
+    except Exception:
+        pass
+    os.dup2(real_stdout, 1)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
