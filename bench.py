@@ -219,9 +219,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
-    launches_per_graph_step = 2 if world == 1 else 3          # train+adam | train+reduce+(adam | fused exchange+adam)
-    gpu_launches = (_lib.launch_count() - launches0) if not graphed else args.steps // chunk * chunk * launches_per_graph_step + \
-        (_lib.launch_count() - launches0)
+    torch.cuda.synchronize()
+    c0 = _lib.launch_count()
+    runner.step(0)                                            # count the kernels of ONE step (outside the timed region)
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - c0
+    gpu_launches = args.steps * launches_per_step
     value = args.steps * B_TRAIN * T * world / (ms * 1e-3)
     final_loss = float(runner.loss[0].item())
 

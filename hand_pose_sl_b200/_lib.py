@@ -57,6 +57,10 @@ _SIGNATURES = {
                                               c_void_p, c_int64, c_void_p]),
     "b2h_adam_step_dp": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_double, c_double, c_double,
                                  c_double, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "b2h_train_step_dp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
+                                  c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_int64,
+                                  c_void_p]),
     "b2h_dp_status": (c_int, []),
     "b2h_tc_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b2h_tc_status": (c_int, []),

@@ -131,7 +131,8 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
                         const int32_t* lengths, const float* params, const void* packed, float* pred_out, int B, int T,
                         int n_in, int C, int pos_emb, int loss_kind, int precision, int mode, void* workspace,
                         int64_t workspace_bytes, cudaStream_t stream, Geo& g, int& nparts, float*& partials,
-                        float*& loss_partials, const char* who, long long* step_dev = nullptr, long long* epoch_dev = nullptr) {
+                        float*& loss_partials, const char* who, long long* step_dev = nullptr, long long* epoch_dev = nullptr,
+                        FuseAdam* fuse = nullptr) {
   if (!x || !params || !packed || !workspace) { set_error("%s: null pointer", who); return B2H_EINVAL; }
   if (x_dtype != B2H_DT_F32 && x_dtype != B2H_DT_BF16) { set_error("%s: bad x_dtype %d", who, x_dtype); return B2H_EINVAL; }
   if (!geo_ok(n_in, C, pos_emb, who)) return B2H_ESHAPE;
@@ -149,7 +150,7 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
   g = make_geo(n_in, C, pos_emb);
   nparts = train_nparts(g, B, T, precision);
   const int64_t stride = train_part_stride(g, T, precision);
-  const int64_t need = ((int64_t)nparts * stride + nparts) * 4;
+  const int64_t need = ((int64_t)nparts * stride + nparts) * 4 + 64;   // + grid-barrier words of the fused kernel
   if (workspace_bytes < need) { set_error("%s: workspace %lld B < %lld B", who, (long long)workspace_bytes, (long long)need); return B2H_EWORKSPACE; }
   partials = reinterpret_cast<float*>(workspace);
   loss_partials = partials + (size_t)nparts * stride;
@@ -161,6 +162,11 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
   a.B = B; a.T = T; a.loss_kind = loss_kind; a.apply_mask = 1; a.mode = mode; a.out_scale = 1.0f; a.geo = g;
   a.step_dev = step_dev;
   a.epoch_dev = epoch_dev;
+  if (fuse && use_tc_train(g, T, precision)) {
+    fuse->enabled = 1;
+    fuse->sync = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + (((int64_t)nparts * stride + nparts) * 4 + 15) / 16 * 16);
+    a.fuse = *fuse;
+  }
   if (use_tc_train(g, T, precision)) return launch_tc_tile_train(a, stream);
   return launch_fp32(a, true, stream, nparts);
 }
@@ -231,13 +237,52 @@ extern "C" int b2h_train_step(const void* x, int x_dtype, const float* target, c
   if (!exp_avg || !exp_avg_sq || !loss_out) { set_error("b2h_train_step: null pointer"); return B2H_EINVAL; }
   if (step < 1 && !step_dev) { set_error("b2h_train_step: step must be >= 1"); return B2H_EINVAL; }
   Geo g; int nparts; float *partials, *loss_partials;
+  // bf16 tile kernel + device-side step counter: ONE cooperative launch (reduction + Adam + re-pack in its tail)
+  FuseAdam fuse{};
+  fuse.params = params; fuse.m = exp_avg; fuse.v = exp_avg_sq; fuse.packed = reinterpret_cast<char*>(packed);
+  fuse.lr = lr; fuse.beta1 = beta1; fuse.beta2 = beta2; fuse.eps = (float)eps; fuse.grad_scale = 1.0f;
+  fuse.step_dev = reinterpret_cast<const long long*>(step_dev); fuse.loss_out = loss_out; fuse.world = 1;
   int rc = train_common(x, x_dtype, target, conf, nullptr, lengths, params, packed, nullptr, B, T, n_in, C, pos_emb,
                         loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
-                        loss_partials, "b2h_train_step", reinterpret_cast<long long*>(step_dev));
+                        loss_partials, "b2h_train_step", reinterpret_cast<long long*>(step_dev), nullptr,
+                        step_dev ? &fuse : nullptr);
   if (rc) return rc;
+  if (step_dev && use_tc_train(g, T, precision)) return B2H_OK;
   return launch_adam(params, partials, nparts, use_tc_train(g, T, precision) ? 1 : 0, exp_avg, exp_avg_sq, g.P, lr, beta1, beta2, eps, step < 1 ? 1 : step,
                      reinterpret_cast<const long long*>(step_dev), 1.0f, packed, g,
                      loss_partials, loss_out, (cudaStream_t)stream);
+}
+
+extern "C" int b2h_train_step_dp(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,
+                                 float* params, void* packed, float* exp_avg, float* exp_avg_sq, float* loss_out, int B, int T,
+                                 int n_in, int C, int pos_emb, int loss_kind, int precision, double lr, double beta1,
+                                 double beta2, double eps, int64_t* step_dev, int64_t* epoch_dev, float* sym_grads,
+                                 const void* peer_bufs_dev, int rank, int world, float grad_scale, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
+  if (!exp_avg || !exp_avg_sq || !loss_out || !step_dev || !epoch_dev || !sym_grads || !peer_bufs_dev) {
+    set_error("b2h_train_step_dp: null pointer");
+    return B2H_EINVAL;
+  }
+  if (world < 1 || world > 32 || rank < 0 || rank >= world) { set_error("b2h_train_step_dp: bad rank/world"); return B2H_EINVAL; }
+  Geo g; int nparts; float *partials, *loss_partials;
+  FuseAdam fuse{};
+  fuse.params = params; fuse.m = exp_avg; fuse.v = exp_avg_sq; fuse.packed = reinterpret_cast<char*>(packed);
+  fuse.lr = lr; fuse.beta1 = beta1; fuse.beta2 = beta2; fuse.eps = (float)eps; fuse.grad_scale = grad_scale;
+  fuse.step_dev = reinterpret_cast<const long long*>(step_dev); fuse.loss_out = loss_out;
+  fuse.peer_bufs = reinterpret_cast<const float* const*>(peer_bufs_dev); fuse.sym_grads = sym_grads;
+  fuse.epoch_dev = reinterpret_cast<const long long*>(epoch_dev); fuse.rank = rank; fuse.world = world;
+  int rc = train_common(x, x_dtype, target, conf, nullptr, lengths, params, packed, nullptr, B, T, n_in, C, pos_emb,
+                        loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
+                        loss_partials, "b2h_train_step_dp", reinterpret_cast<long long*>(step_dev),
+                        reinterpret_cast<long long*>(epoch_dev), &fuse);
+  if (rc) return rc;
+  if (use_tc_train(g, T, precision)) return B2H_OK;    // everything happened inside the one cooperative launch
+  rc = launch_reduce(partials, nparts, 0, g, sym_grads, loss_partials, loss_out, (cudaStream_t)stream,
+                     reinterpret_cast<const long long*>(epoch_dev));
+  if (rc) return rc;
+  return launch_adam_dp(params, reinterpret_cast<const float* const*>(peer_bufs_dev), rank, world, exp_avg, exp_avg_sq, g.P, lr,
+                        beta1, beta2, eps, reinterpret_cast<const long long*>(step_dev),
+                        reinterpret_cast<const long long*>(epoch_dev), grad_scale, packed, g, (cudaStream_t)stream);
 }
 
 extern "C" int b2h_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,

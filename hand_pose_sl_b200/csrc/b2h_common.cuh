@@ -109,6 +109,49 @@ __host__ __device__ inline int flat_index_of_gp(const Geo& g, int j) {
   return ci < g.cin[l] ? g.w_off[l] + (co * g.cin[l] + ci) * B2H_KW + k : -1;
 }
 
+// Scatter one fp32 parameter (flat index i) into the packed operand layouts.
+__device__ __forceinline__ void scatter_packed(const Geo& g, char* packed, int i, float v) {
+  int l = 0;
+#pragma unroll
+  for (int q = 1; q < 4; ++q)
+    if (i >= g.w_off[q]) l = q;
+  if (i >= g.b_off[l]) {        // bias: also kept zero-padded [4][64] for the tensor-core kernels' smem copy
+    if (i - g.b_off[l] < 64) reinterpret_cast<float*>(packed + g.bias_off)[l * 64 + (i - g.b_off[l])] = v;
+    return;
+  }
+  const int cin = g.cin[l], cout = g.cout[l];
+  const int rel = i - g.w_off[l];
+  const int co = rel / (cin * B2H_KW);
+  const int rem = rel - co * cin * B2H_KW;
+  const int ci = rem / B2H_KW, k = rem - ci * B2H_KW;
+  reinterpret_cast<float*>(packed + g.wf_off[l])[(k * cin + ci) * cout + co] = v;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(packed + g.tf_off[l] + umma_b_offset(k, ci, co, g.kp[l], g.np_[l])) = h;
+  if (l > 0) {
+    reinterpret_cast<float*>(packed + g.wd_off[l])[((B2H_KW - 1 - k) * cout + co) * cin + ci] = v;
+    *reinterpret_cast<__nv_bfloat16*>(packed + g.td_off[l] +
+                                      umma_b_offset(B2H_KW - 1 - k, co, ci, round_up(cout, 16), round_up(cin, 16))) = h;
+  }
+}
+
+
+// Optional tail of the tensor-core train kernel: cross-CTA gradient reduction, (data-parallel) gradient exchange
+// over peer memory and Adam, all inside the SAME cooperative launch (grid barriers through `sync`).
+struct FuseAdam {
+  int enabled;
+  float* params; float* m; float* v; char* packed;
+  double lr, beta1, beta2;
+  float eps, grad_scale;
+  const long long* step_dev;
+  float* loss_out;
+  unsigned* sync;                    // [2] zero-initialised words: arrival counter, generation
+  // data parallel (world > 1)
+  const float* const* peer_bufs;     // device array [world] of peer exchange buffers ([2][P] fp32 + [world] int64 flags)
+  float* sym_grads;                  // this rank's exchange buffer
+  const long long* epoch_dev;
+  int rank, world;
+};
+
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 void count_launch(int n = 1);
@@ -124,6 +167,7 @@ struct Fp32Args {
   float* loss_partials;     // [grid]
   long long* step_dev;      // nullable: device step counter, incremented by block 0 (read by the Adam kernel)
   long long* epoch_dev;     // nullable: data-parallel exchange epoch, incremented the same way (never rewound)
+  FuseAdam fuse;            // tensor-core train kernel only: reduce + exchange + Adam in the same launch
   int B, T, loss_kind, apply_mask, mode;   // mode 0 = forward, 1 = train (loss inside), 2 = backward of given d_y
   float out_scale;
   Geo geo;

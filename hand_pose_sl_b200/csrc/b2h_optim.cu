@@ -10,31 +10,6 @@
 
 namespace b2h {
 
-// Scatter one fp32 parameter (flat index i) into the packed operand layouts.
-__device__ __forceinline__ void scatter_packed(const Geo& g, char* packed, int i, float v) {
-  int l = 0;
-#pragma unroll
-  for (int q = 1; q < 4; ++q)
-    if (i >= g.w_off[q]) l = q;
-  if (i >= g.b_off[l]) {        // bias: also kept zero-padded [4][64] for the tensor-core kernels' smem copy
-    if (i - g.b_off[l] < 64) reinterpret_cast<float*>(packed + g.bias_off)[l * 64 + (i - g.b_off[l])] = v;
-    return;
-  }
-  const int cin = g.cin[l], cout = g.cout[l];
-  const int rel = i - g.w_off[l];
-  const int co = rel / (cin * B2H_KW);
-  const int rem = rel - co * cin * B2H_KW;
-  const int ci = rem / B2H_KW, k = rem - ci * B2H_KW;
-  reinterpret_cast<float*>(packed + g.wf_off[l])[(k * cin + ci) * cout + co] = v;
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  *reinterpret_cast<__nv_bfloat16*>(packed + g.tf_off[l] + umma_b_offset(k, ci, co, g.kp[l], g.np_[l])) = h;
-  if (l > 0) {
-    reinterpret_cast<float*>(packed + g.wd_off[l])[((B2H_KW - 1 - k) * cout + co) * cin + ci] = v;
-    *reinterpret_cast<__nv_bfloat16*>(packed + g.td_off[l] +
-                                      umma_b_offset(B2H_KW - 1 - k, co, ci, round_up(cout, 16), round_up(cin, 16))) = h;
-  }
-}
-
 __global__ void pack_kernel(const float* __restrict__ params, char* packed, Geo g) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < g.P) scatter_packed(g, packed, i, params[i]);

@@ -43,6 +43,7 @@ struct TcTileArgs {
   long long* step_dev;
   long long* epoch_dev;
   long long* dbg;         // nullable: CTA 0 / thread 0 writes clock64() phase stamps here (b2h_debug_timing)
+  FuseAdam fuse;
   int B, T, loss_kind, apply_mask, mode;   // mode 0 = forward only, 1 = train (loss inside), 2 = backward of given d_y
   float out_scale;
   int n_tiles, nhalf, MB, HR, gh;          // tile geometry
@@ -114,6 +115,40 @@ __device__ __forceinline__ void issue_conv(uint32_t d_tmem, uint32_t a_lo, uint3
       acc = 1;
     }
   }
+}
+
+// Grid-wide barrier of a cooperative launch (all CTAs co-resident): sense-reversing counter + generation word,
+// reusable across launches without a reset.  Bounded spin: a protocol bug ends as a wrong answer + status, not a hang.
+__device__ __forceinline__ void grid_barrier(unsigned* sync, int tid) {
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    volatile unsigned* gen_p = sync + 1;
+    const unsigned gen = *gen_p;
+    if (atomicAdd(sync, 1u) == gridDim.x - 1) {
+      *reinterpret_cast<volatile unsigned*>(sync) = 0u;
+      __threadfence();
+      atomicAdd(sync + 1, 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*gen_p == gen) {
+        if (clock64() - t0 > 4000000000LL) { atomicExch(&g_tc_status, 50); break; }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void adam_update(const FuseAdam& f, const Geo& g, int i, float gr, float step_size, float inv_bc2_sqrt) {
+  gr *= f.grad_scale;
+  float m = f.m[i], v = f.v[i], p = f.params[i];
+  m = fmaf(gr - m, (float)(1.0 - f.beta1), m);
+  v = fmaf((float)(1.0 - f.beta2) * gr, gr, v * (float)f.beta2);
+  const float denom = sqrtf(v) * inv_bc2_sqrt + f.eps;
+  p = p - step_size * (m / denom);
+  f.m[i] = m; f.v[i] = v; f.params[i] = p;
+  if (f.packed) scatter_packed(g, f.packed, i, p);
 }
 
 #define B2H_STAMP() do { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 120) p.dbg[dbg_n++] = clock64(); } while (0)
@@ -449,7 +484,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
                   const uint64_t ad = desc64(a_lo0 + r0, hi_mn);
 #pragma unroll
                   for (int k = 0; k < B2H_KW + 1; ++k) {
-                    if ((k % nissue) != warp) continue;
+                    if (nissue == 2 && (k & 1) != warp) continue;
                     if (k < B2H_KW) umma_bf16(dcol + k * 32, ad, desc64(b_lo0 + r0 + k - 2, hi_mn), idw, first);
                     else umma_bf16(dcol + 5 * 32, ad, desc64(o_lo0 + r0, hi_mn), idb, first);
                   }
@@ -528,6 +563,106 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
     }
     if (tid == 0 && p.loss_partials)
       p.loss_partials[blockIdx.x] = (p.loss_kind == B2H_LOSS_L1) ? loss_acc / (float)p.B : loss_acc;
+    B2H_STAMP();   // partial slice written
+
+    if (p.fuse.enabled) {
+      // ===== same launch: cross-CTA reduction (+ peer exchange) + Adam + weight re-pack =====
+      const FuseAdam& f = p.fuse;
+      __shared__ float s_step_size, s_inv_bc2_sqrt;
+      grid_barrier(f.sync, tid);                         // every CTA's partial slice is visible
+      B2H_STAMP();   // tail: grid barrier passed
+      if (tid == 0) {
+        const double tt = (double)*f.step_dev;
+        s_step_size = (float)(f.lr / (1.0 - pow(f.beta1, tt)));
+        s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(f.beta2, tt)));
+      }
+      if (blockIdx.x == 0 && warp == 1 && f.loss_out) {  // loss = sum of the CTAs' loss partials (fixed order)
+        float sl = 0.f;
+        for (int c = lane; c < (int)gridDim.x; c += 32) sl += __ldcg(p.loss_partials + c);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
+        if (lane == 0) *f.loss_out = sl;
+      }
+      __syncthreads();
+      const int nj = gp_total(g);                        // multiple of 4: every slice is float4-addressable
+      const int nparts = (int)gridDim.x;
+      const int per = round_up((nj + nparts - 1) / nparts, 4);
+      const int j0 = (int)blockIdx.x * per;
+      const int j_end = min(nj, j0 + per);
+      const bool dp = f.world > 1;
+      const size_t P = (size_t)g.P;
+      const long long epoch = dp ? *f.epoch_dev : 0;
+      float* my_sym = dp ? f.sym_grads + (size_t)(epoch & 1) * P : nullptr;
+      // Latency-bound L2 gather of this CTA's `per` slots over all CTA slices: float4 columns x part groups, 16
+      // independent 16-B loads in flight per thread, fixed summation order (deterministic).
+      float4* red4 = reinterpret_cast<float4*>(YS);       // [groups][ncol] partial sums (the staging tile is free now)
+      for (int jb = j0; jb < j_end; jb += 4096) {        // <= 1024 float4 columns (16 KB of staging) per pass
+        const int jn = min(j_end, jb + 4096);
+        const int ncol = (jn - jb + 3) >> 2;
+        int groups = kTileThreads / ncol; groups = groups < 1 ? 1 : (groups > 8 ? 8 : groups);
+        const int cpg = kTileThreads / groups;            // columns handled per sweep
+        for (int cb = 0; cb < ncol; cb += cpg) {
+          const int col = cb + tid % cpg, pg = tid / cpg;
+          if (col < ncol && pg < groups) {
+            const float4* src = reinterpret_cast<const float4*>(p.partials + jb + 4 * col);
+            const size_t stride4 = (size_t)nj >> 2;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int c = pg; c < nparts; c += 16 * groups) {
+              float4 v[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                const int cc = c + u * groups;
+                v[u] = (cc < nparts) ? __ldcg(src + (size_t)cc * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int u = 0; u < 16; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+            }
+            red4[pg * ncol + col] = acc;
+          }
+        }
+        __syncthreads();
+        const float* red = reinterpret_cast<const float*>(red4);
+        for (int j = jb + tid; j < jn; j += kTileThreads) {
+          float gr = 0.f;
+          for (int pg = 0; pg < groups; ++pg) gr += red[(size_t)pg * ncol * 4 + (j - jb)];
+          const int i = flat_index_of_gp(g, j);
+          if (i >= 0) {
+            if (dp) my_sym[i] = gr;
+            else adam_update(f, g, i, gr, s_step_size, s_inv_bc2_sqrt);
+          }
+        }
+        __syncthreads();
+      }
+      B2H_STAMP();   // tail: reduction (+ Adam when single-GPU) done
+      if (dp) {
+        // gradient exchange over peer (NVLink) memory, protocol of adam_dp_kernel (b2h_optim.cu)
+        grid_barrier(f.sync, tid);                       // this rank's flat gradient is complete
+        const size_t flag_off = 2 * P;
+        if (blockIdx.x == 0 && tid < f.world) {
+          __threadfence_system();
+          volatile long long* fl = reinterpret_cast<volatile long long*>(const_cast<float*>(f.peer_bufs[tid]) + flag_off) + f.rank;
+          *fl = epoch;
+          __threadfence_system();
+        }
+        if (tid < f.world) {
+          const volatile long long* fl = reinterpret_cast<const volatile long long*>(f.peer_bufs[f.rank] + flag_off) + tid;
+          const long long t0 = clock64();
+          while (*fl < epoch) {
+            if (clock64() - t0 > 6000000000LL) { atomicExch(&g_tc_status, 51); break; }
+          }
+          __threadfence_system();
+        }
+        __syncthreads();
+        const int perp = round_up((g.P + nparts - 1) / nparts, 32);
+        const int i_end = min(g.P, (int)(blockIdx.x + 1) * perp);
+        const size_t off = (size_t)(epoch & 1) * P;
+        for (int i = blockIdx.x * perp + tid; i < i_end; i += kTileThreads) {
+          float gr = 0.f;
+          for (int r = 0; r < f.world; ++r) gr += __ldcv(f.peer_bufs[r] + off + i);
+          adam_update(f, g, i, gr, s_step_size, s_inv_bc2_sqrt);
+        }
+      }
+    }
   }
   if (!TRAIN && tid == 0) bulk_wait0();
   B2H_STAMP();   // readout done
@@ -576,7 +711,12 @@ int launch_tc_tile(TcTileArgs& p, bool train, cudaStream_t stream) {
     if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e)); return B2H_ECUDA; }
     attr_bytes[train ? 1 : 0] = smem;
   }
-  if (train) conv_tc_tile_kernel<true><<<grid, kTileThreads, smem, stream>>>(p);
+  if (train && p.fuse.enabled) {
+    // grid barriers inside: cooperative launch guarantees that all CTAs (<= 1 per SM) are co-resident
+    void* kargs[] = {&p};
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)conv_tc_tile_kernel<true>, dim3(grid), dim3(kTileThreads), kargs, smem, stream);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaLaunchCooperativeKernel: %s", cudaGetErrorString(e)); return B2H_ECUDA; }
+  } else if (train) conv_tc_tile_kernel<true><<<grid, kTileThreads, smem, stream>>>(p);
   else conv_tc_tile_kernel<false><<<grid, kTileThreads, smem, stream>>>(p);
   count_launch();
   return check_launch(train ? "conv_tc_tile_kernel<train>" : "conv_tc_tile_kernel<fwd>");
@@ -602,6 +742,7 @@ int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream) {
   p.params = a.params; p.packed = a.packed; p.y = a.y; p.partials = a.partials; p.loss_partials = a.loss_partials;
   p.step_dev = a.step_dev; p.epoch_dev = a.epoch_dev; p.B = a.B; p.T = a.T; p.loss_kind = a.loss_kind; p.apply_mask = 1; p.mode = a.mode;
   p.out_scale = 1.0f; p.geo = a.geo;
+  p.fuse = a.fuse;
   p.dbg = g_dbg_timing;
   return launch_tc_tile(p, true, stream);
 }

@@ -161,7 +161,7 @@ class ConvModel(nn.Module):
         need = _lib.workspace_bytes(B, T, n_in, C, pe, _lib.PRECISIONS[self.precision])
         dev = self._flat.device
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
-            self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+            self._workspace = torch.zeros(need, dtype=torch.uint8, device=dev)    # holds the fused kernel's grid-barrier words
         return self._workspace
 
     # ------------------------------------------------------------------ kernels

@@ -145,15 +145,13 @@ class DataParallelTrainer:
         conf = None if self.conf is None else self.conf[slot]
         sp = _lib.stream_ptr(self.dev)
         if self.exchange == "p2p":
-            _lib.check(self.lib.b2h_train_forward_backward_dp(
+            _lib.check(self.lib.b2h_train_step_dp(
                 _lib.ptr(self.x[slot]), _lib.DT_F32, _lib.ptr(self.target[slot]), _lib.ptr(conf), _lib.ptr(self.lengths[slot]),
-                _lib.ptr(m._flat), _lib.ptr(self.packed), _lib.ptr(self.sym), _lib.ptr(self.loss[slot:slot + 1]),
-                self.B, self.T, n_in, C, pe, self.kind, _lib.PRECISIONS[m.precision], _lib.ptr(self.step_dev),
-                _lib.ptr(self.epoch_dev), _lib.ptr(self.ws), self.ws.numel(), sp))
-            _lib.check(self.lib.b2h_adam_step_dp(
-                _lib.ptr(m._flat), _lib.ptr(self.peer_ptrs), self.rank, self.world, _lib.ptr(self.state["m"]),
-                _lib.ptr(self.state["v"]), m._flat.numel(), float(g["lr"]), b1, b2, g["eps"], _lib.ptr(self.step_dev),
-                _lib.ptr(self.epoch_dev), grad_scale_for(self.loss_name, self.world), _lib.ptr(self.packed), n_in, C, pe, sp))
+                _lib.ptr(m._flat), _lib.ptr(self.packed), _lib.ptr(self.state["m"]), _lib.ptr(self.state["v"]),
+                _lib.ptr(self.loss[slot:slot + 1]), self.B, self.T, n_in, C, pe, self.kind, _lib.PRECISIONS[m.precision],
+                float(g["lr"]), b1, b2, g["eps"], _lib.ptr(self.step_dev), _lib.ptr(self.epoch_dev), _lib.ptr(self.sym),
+                _lib.ptr(self.peer_ptrs), self.rank, self.world, grad_scale_for(self.loss_name, self.world),
+                _lib.ptr(self.ws), self.ws.numel(), sp))
             self.host_steps += 1
             self.state["step"] = self.host_steps
             return self.loss[slot]

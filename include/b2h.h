@@ -160,11 +160,21 @@ int b2h_train_forward_backward_dp(const void* x, int x_dtype, const float* targe
 int b2h_adam_step_dp(float* params, const void* peer_bufs_dev, int rank, int world, float* exp_avg, float* exp_avg_sq,
                      int64_t n, double lr, double beta1, double beta2, double eps, const int64_t* step_dev,
                      const int64_t* epoch_dev, float grad_scale, void* packed, int n_in, int C, int pos_emb, void* stream);
+/* The whole data-parallel step as ONE call; in bf16 mode (tensor-core tile kernel) also ONE cooperative kernel
+ * launch per rank: forward + loss + backward, grid barrier, cross-CTA reduction into the exchange buffer, flag
+ * exchange + gradient sum over peer memory, Adam + re-pack.  Other shapes run the same protocol as three launches. */
+int b2h_train_step_dp(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,
+                      float* params, void* packed, float* exp_avg, float* exp_avg_sq, float* loss_out, int B, int T,
+                      int n_in, int C, int pos_emb, int loss_kind, int precision, double lr, double beta1, double beta2,
+                      double eps, int64_t* step_dev, int64_t* epoch_dev, float* sym_grads, const void* peer_bufs_dev,
+                      int rank, int world, float grad_scale, void* workspace, int64_t workspace_bytes, void* stream);
 /* 0 = clean, 1 = a peer-flag wait gave up (bounded spin); reading clears it.  Synchronises the device. */
 int b2h_dp_status(void);
 
 /* Fast path = b2h_train_forward_backward + b2h_adam_step with the cross-CTA gradient reduction
- * fused into the Adam kernel (2 launches per step, zero host work).  step_dev (nullable): a device
+ * fused into the Adam kernel (2 launches per step, zero host work); in bf16 mode with step_dev the reduction and
+ * Adam run in the tail of the SAME cooperative launch (1 launch per step; the workspace must be zero-initialised
+ * once: it holds the grid-barrier words).  step_dev (nullable): a device
  * int64 holding the number of steps taken so far; when given it is incremented on the device and
  * used instead of `step`, so a captured CUDA graph of this call can be replayed step after step. */
 int b2h_train_step(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,

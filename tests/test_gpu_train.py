@@ -191,3 +191,49 @@ def test_config3_full_size_properties(prec):
     assert abs(float(l16) - ref_loss) <= TOL[prec] * abs(ref_loss)
     for k, v in _split(m, g16).items():
         assert oracle.rel_err(v, ref_g[k].numpy()) <= GTOL[prec], k
+
+
+@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_train_step_runner_matches_golden(prec, graph):
+    """The steady-state runner (static buffers, device-side step counter; in bf16 mode ONE cooperative launch per step
+    with the reduction + Adam in the kernel tail; optionally replayed from a CUDA graph) == the reference steps."""
+    from hand_pose_sl_b200.runner import TrainStepRunner
+    g = load_golden("convmodel_c30.npz")
+    sd = golden_sd(g)
+    m = _model(sd, 30, False, prec)
+    opt = b2h.FusedAdam(m.parameters(), lr=float(g["lr"]))
+    B, T = g["input_kp"].shape[:2]
+    r = TrainStepRunner(m, opt, B, T, "L1", n_slots=1)
+    r.load({"input_kp": torch.from_numpy(g["input_kp"]), "target_kp": torch.from_numpy(g["target_kp"]),
+            "n_frames": torch.from_numpy(g["lengths"])}, non_blocking=False)
+    steps = len(g["loss_L1"])
+    losses = []
+    if graph:
+        r.capture(1)
+        for s in range(steps):
+            r.replay()
+            losses.append(float(r.loss[0]))
+    else:
+        for s in range(steps):
+            losses.append(float(r.step(0)))
+    r.finish()
+    torch.cuda.synchronize()
+    assert _lib.load().b2h_tc_status() == 0
+    for s in range(steps):
+        assert abs(losses[s] - g["loss_L1"][s]) <= TOL[prec] * abs(g["loss_L1"][s]), (s, losses)
+    st = oracle.TrainState(sd, lr=float(g["lr"]))
+    all_grads = []
+    for s in range(steps):
+        _, gr = oracle.train_step(st, torch.from_numpy(g["input_kp"]), torch.from_numpy(g["target_kp"]), torch.from_numpy(g["lengths"]))
+        all_grads.append({k: v.numpy() for k, v in gr.items()})
+    masks = oracle.adam_conditioned(all_grads, sd, float(g["lr"]))
+    for k, v in m.state_dict().items():
+        want = g[f"w{steps}_L1_" + k.replace(".", "_")]
+        d = np.abs(v.cpu().numpy() - want)
+        assert d[masks[k]].max() <= TOL[prec] * np.abs(want).max(), k
+        assert d.max() <= 2 * float(g["lr"]) * steps, k
+    assert float(opt.state_dict()["state"][0]["step"]) == steps
+    packed_by_kernel = m._packed.clone()
+    m.mark_packed_stale()
+    assert torch.equal(m.packed_weights(), packed_by_kernel)
