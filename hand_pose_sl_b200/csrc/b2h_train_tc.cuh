@@ -259,6 +259,38 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   const uint32_t hi_mn = desc_hi((uint32_t)CH);  // MN-major operands: SBO = chunk stride
   const uint32_t acc_d = tbase + kAccCol;
 
+  // Read one layer pair's weight / bias gradient accumulators out into this CTA's partial slice.  A pair shares its
+  // TMEM columns: lanes 32q+i hold layer 2p (co = 16q+i), lanes 32q+16+i layer 2p+1, so one tcgen05.ld per tap
+  // serves both layers and every lane has a row to store.
+  bool pair1_done = false;
+  auto readout_pair = [&](int pr) {
+    float* part = p.partials + (size_t)blockIdx.x * gp_total(g);
+    const int l = 2 * pr + (lane >> 4);
+    const int co = warp * 16 + (lane & 15);
+    const bool mine = co < g.cout[l];
+    const int Nw = g.kp[l];
+    float* lp = part + gp_layer_off(g, l);
+    const uint32_t dcol = tbase + lane_addr + kWgCol + pr * kWgPairCols;
+    uint32_t v[B2H_KW][32];
+#pragma unroll
+    for (int k = 0; k < B2H_KW; ++k) tmem_ld32(dcol + k * 32, v[k]);
+    uint32_t vb[16];
+    tmem_ld16(dcol + 5 * 32, vb);      // 8 valid columns; column 0 holds db (ones sits in element 0)
+    tmem_ld_wait();
+    if (mine) {
+#pragma unroll
+      for (int k = 0; k < B2H_KW; ++k) {
+        float4* dst = reinterpret_cast<float4*>(lp + ((size_t)k * g.cout[l] + co) * Nw);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q * 4 < Nw)
+            dst[q] = make_float4(__uint_as_float(v[k][4 * q]), __uint_as_float(v[k][4 * q + 1]), __uint_as_float(v[k][4 * q + 2]),
+                                 __uint_as_float(v[k][4 * q + 3]));
+      }
+      lp[B2H_KW * g.cout[l] * Nw + co] = __uint_as_float(vb[0]);
+    }
+  };
+
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int wbase = tile * wpt;
     const int gw = wbase + hh * gh + wj;           // this thread's global window
@@ -375,14 +407,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           n_el = (float)len * (float)B2H_COUT;
           scale = (p.loss_kind == B2H_LOSS_L1) ? (1.0f / (float)p.B) / n_el : 1.0f / n_el;
           if (p.mode == 1) {
-            tg = tgt_smem ? YS + (size_t)srow * B2H_COUT : p.target + ((size_t)gw * T + t) * B2H_COUT;
+            tg = p.target + ((size_t)gw * T + t) * B2H_COUT;        // global copy (used when the tile is not staged)
             cf = p.conf ? p.conf + ((size_t)gw * T + t) * (B2H_COUT / 2) : nullptr;
           } else {
             dy = p.d_y + ((size_t)gw * T + t) * B2H_COUT;
           }
         }
         const bool y_smem = !TRAIN && bulk_io;
-        float* yrow = (valid && p.y) ? (y_smem ? YS + (size_t)srow * B2H_COUT : p.y + ((size_t)gw * T + t) * B2H_COUT) : nullptr;
+        float* yrow = (valid && p.y) ? p.y + ((size_t)gw * T + t) * B2H_COUT : nullptr;          // global row
+        float* ys_row = YS + (size_t)srow * B2H_COUT;                                            // shared staging row
         if (tgt_smem) { mbar_wait(&tbar, tphase, 18); tphase ^= 1; }
         B2H_STAMP();   // layer-4 epilogue: target tile landed
         float sum = 0.f;
@@ -391,42 +424,58 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
           float gq[16];
+          if (!TRAIN) {
+            // inference epilogue: bias, optional mask_output (utils.py:309-312) / de-normalise, store the row
+            const bool masked = p.apply_mask && (t >= len);
 #pragma unroll
-          for (int q = 0; q < 16; q += 2) {
-            const int c = c0 + q;
-            float ga = 0.f, gb = 0.f;
-            if (valid && c < B2H_COUT) {
-              float a = __uint_as_float(v[q]) + bias_s[3][c];
-              float b = __uint_as_float(v[q + 1]) + bias_s[3][c + 1];
-              const bool masked = (TRAIN || p.apply_mask) && (t >= len);       // mask_output  utils.py:309-312
-              if (masked) { a = 0.0f; b = 0.0f; }
-              else if (!TRAIN && p.out_scale != 1.0f) { a *= p.out_scale; b *= p.out_scale; }
-              if (yrow) *reinterpret_cast<float2*>(yrow + c) = make_float2(a, b);
-              if (TRAIN && !masked) {
-                if (p.mode == 1) {
-                  const float2 tv = *reinterpret_cast<const float2*>(tg + c);
-                  float da, db, s = 1.0f;
-                  if (p.loss_kind == B2H_LOSS_L1) { da = a - tv.x; db = b - tv.y; }     // utils.py:422-426
-                  else {
-                    s = __ldg(cf + (c >> 1));
-                    da = __fsub_rn(__fmul_rn(a, s), __fmul_rn(tv.x, s));                 // utils.py:447-450
-                    db = __fsub_rn(__fmul_rn(b, s), __fmul_rn(tv.y, s));
-                  }
-                  sum += fabsf(da) + fabsf(db);
-                  ga = (da > 0.f ? 1.f : (da < 0.f ? -1.f : 0.f)) * s * scale;
-                  gb = (db > 0.f ? 1.f : (db < 0.f ? -1.f : 0.f)) * s * scale;
-                } else {
-                  const float2 d2 = __ldg(reinterpret_cast<const float2*>(dy + c));
-                  ga = d2.x; gb = d2.y;
-                }
+            for (int q = 0; q < 16; q += 2) {
+              const int c = c0 + q;
+              if (yrow && c < B2H_COUT) {
+                float a = __uint_as_float(v[q]) + bias_s[3][c];
+                float b = __uint_as_float(v[q + 1]) + bias_s[3][c + 1];
+                if (masked) { a = 0.0f; b = 0.0f; }
+                else if (p.out_scale != 1.0f) { a *= p.out_scale; b *= p.out_scale; }
+                if (y_smem) *reinterpret_cast<float2*>(ys_row + c) = make_float2(a, b);
+                else *reinterpret_cast<float2*>(yrow + c) = make_float2(a, b);
               }
             }
-            gq[q] = ga; gq[q + 1] = gb;
+          } else {
+            // training epilogue, branch-free per element: masked prediction, criterion term, d(loss)/d(pred).
+            // L1 is the confidence-weighted form with s = 1 (a*1 - t*1 == a - t exactly).   utils.py:422-426 / :447-450
+            const bool live = valid && (t < len);          // rows t >= len are zeroed by mask_output and carry no loss
+            float tvals[16], svals[16];
+#pragma unroll
+            for (int q = 0; q < 16; q += 2) {
+              float2 tv2 = make_float2(0.f, 0.f);
+              float sv = 1.0f;
+              if (live && c0 + q < B2H_COUT) {
+                if (p.mode == 1) tv2 = tgt_smem ? *reinterpret_cast<const float2*>(ys_row + c0 + q) : __ldg(reinterpret_cast<const float2*>(tg + c0 + q));
+                else tv2 = __ldg(reinterpret_cast<const float2*>(dy + c0 + q));
+                if (cf && p.loss_kind == B2H_LOSS_CONFL1) sv = __ldg(cf + ((c0 + q) >> 1));
+              }
+              tvals[q] = tv2.x; tvals[q + 1] = tv2.y; svals[q] = sv; svals[q + 1] = sv;
+            }
+            const bool given_dy = (p.mode != 1);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int c = c0 + q;
+              const bool on = live && (c < B2H_COUT);
+              const float a = on ? __uint_as_float(v[q]) + bias_s[3][c < 64 ? c : 63] : 0.0f;      // masked prediction
+              const float sv = svals[q];
+              const float d = __fsub_rn(__fmul_rn(a, sv), __fmul_rn(tvals[q], sv));
+              sum += on ? fabsf(d) : 0.0f;
+              const float sc = sv * scale;
+              float gr = d > 0.f ? sc : (d < 0.f ? -sc : 0.f);
+              gr = given_dy ? tvals[q] : gr;                // backward of a given d_y: the staged value IS the gradient
+              gq[q] = on ? gr : 0.0f;
+              if (yrow && c < B2H_COUT && valid) yrow[c] = a;
+            }
           }
           if (TRAIN) {
             store8_bf16(G0, CH, row, c0 >> 3, gq);
             store8_bf16(G0, CH, row, (c0 >> 3) + 1, gq + 8);
           }
+          B2H_STAMP();   // layer-4 epilogue: one 16-column chunk done
         }
         if (TRAIN && p.mode == 1) {
           // per-sample mean = sum_{t<len} |d| / (len*42)  (utils.py:426 / :450): accumulate sum/n_el
@@ -516,6 +565,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
             store8_bf16(gnext, CH, row, (c0 >> 3) + 1, f + 8);
           }
         }
+        if (l == 1 && tile + (int)gridDim.x >= p.n_tiles) {
+          // last tile of this CTA: W_4 and W_3 (layer pair 1) are final (their MMAs precede the commit just waited
+          // on) -> read them out now, under the tensor-pipe time of W_2 / W_1 instead of after the loop
+          readout_pair(1);
+          pair1_done = true;
+        }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -527,39 +582,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   }
 
   if (TRAIN) {
-    // ---- read the weight / bias gradient accumulators out into this CTA's partial slice ----
-    // A layer pair shares its TMEM columns: lanes 32q+i hold layer 2p (co = 16q+i), lanes 32q+16+i layer 2p+1,
-    // so one tcgen05.ld per tap serves both layers and every lane has a row to store.
-    float* part = p.partials + (size_t)blockIdx.x * gp_total(g);
+    // ---- read the remaining weight / bias gradient accumulators out into this CTA's partial slice ----
     if (!wg_started) {
+      float* part = p.partials + (size_t)blockIdx.x * gp_total(g);
       for (int i = tid; i < gp_total(g); i += kTileThreads) part[i] = 0.0f;
     } else {
-      for (int pr = 0; pr < 2; ++pr) {
-        const int l = 2 * pr + (lane >> 4);
-        const int co = warp * 16 + (lane & 15);
-        const bool mine = co < g.cout[l];
-        const int Nw = g.kp[l];
-        float* lp = part + gp_layer_off(g, l);
-        const uint32_t dcol = tbase + lane_addr + kWgCol + pr * kWgPairCols;
-        uint32_t v[B2H_KW][32];
-#pragma unroll
-        for (int k = 0; k < B2H_KW; ++k) tmem_ld32(dcol + k * 32, v[k]);
-        uint32_t vb[16];
-        tmem_ld16(dcol + 5 * 32, vb);      // 8 valid columns; column 0 holds db (ones sits in element 0)
-        tmem_ld_wait();
-        if (mine) {
-#pragma unroll
-          for (int k = 0; k < B2H_KW; ++k) {
-            float4* dst = reinterpret_cast<float4*>(lp + ((size_t)k * g.cout[l] + co) * Nw);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (q * 4 < Nw)
-                dst[q] = make_float4(__uint_as_float(v[k][4 * q]), __uint_as_float(v[k][4 * q + 1]), __uint_as_float(v[k][4 * q + 2]),
-                                     __uint_as_float(v[k][4 * q + 3]));
-          }
-          lp[B2H_KW * g.cout[l] * Nw + co] = __uint_as_float(vb[0]);
-        }
-      }
+      readout_pair(0);
+      if (!pair1_done) readout_pair(1);
     }
     if (tid == 0 && p.loss_partials)
       p.loss_partials[blockIdx.x] = (p.loss_kind == B2H_LOSS_L1) ? loss_acc / (float)p.B : loss_acc;
