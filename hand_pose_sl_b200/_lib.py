@@ -61,6 +61,7 @@ _SIGNATURES = {
                                   c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
                                   c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_int64,
                                   c_void_p]),
+    "b2h_dp_exchange_floats": (c_int64, [c_int, c_int, c_int, c_int]),
     "b2h_dp_status": (c_int, []),
     "b2h_tc_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b2h_tc_status": (c_int, []),

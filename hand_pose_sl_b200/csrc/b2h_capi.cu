@@ -215,6 +215,15 @@ extern "C" int b2h_adam_step_dp(float* params, const void* peer_bufs_dev, int ra
                         grad_scale, packed, g, (cudaStream_t)stream);
 }
 
+extern "C" int64_t b2h_dp_exchange_floats(int n_in, int C, int pos_emb, int world) {
+  if (!geo_ok(n_in, C, pos_emb, "b2h_dp_exchange_floats")) return B2H_ESHAPE;
+  if (world < 1 || world > 32) { set_error("b2h_dp_exchange_floats: bad world"); return B2H_EINVAL; }
+  Geo g = make_geo(n_in, C, pos_emb);
+  // tensor-core path: uint64 words [2][world][slots] (= 4*world*slots floats); the three-launch path needs
+  // [2][P] fp32 + [world] int64 flags, which is smaller
+  return 4 * (int64_t)world * gp_total(g) + 64;
+}
+
 extern "C" int b2h_dp_status(void) { return dp_status_and_clear(); }
 
 extern "C" int b2h_conv_backward(const void* x, int x_dtype, const float* d_y, const float* params, const void* packed,

@@ -54,6 +54,7 @@ constexpr int kTileThreads = 128;
 constexpr int kAccCol = 0;        // forward / dgrad accumulator: columns [0, 64)
 constexpr int kWgCol = 64;        // weight-gradient accumulators: 2 layer pairs x (5 taps x 32 + 8 bias) columns
 constexpr int kWgPairCols = 5 * 32 + 8;
+constexpr int kDpMaxCta = 160;    // flag slots per rank in the data-parallel exchange buffer (>= CTAs of the train kernel)
 
 struct TileSmem {   // byte offsets into dynamic smem
   int g0, g1, x, a1, a2, a3, ones, ys, wf[4], wd[4], total;
@@ -621,7 +622,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       const bool dp = f.world > 1;
       const size_t P = (size_t)g.P;
       const long long epoch = dp ? *f.epoch_dev : 0;
-      float* my_sym = dp ? f.sym_grads + (size_t)(epoch & 1) * P : nullptr;
+      // Data-parallel exchange buffer (per rank, peer-mapped): uint64 words [2 (epoch parity)][world (source rank)][nj],
+      // each word = {fp32 gradient slot, 32-bit epoch tag} written with ONE 8-byte store ("LL" protocol): the tag
+      // travels with the data, so there are no flags, no fences and no second grid barrier.
+      const uint32_t tag = (uint32_t)epoch;
+      const size_t ll_src = ((size_t)(epoch & 1) * f.world + f.rank) * nj;
       // Latency-bound L2 gather of this CTA's `per` slots over all CTA slices: float4 columns x part groups, 16
       // independent 16-B loads in flight per thread, fixed summation order (deterministic).
       float4* red4 = reinterpret_cast<float4*>(YS);       // [groups][ncol] partial sums (the staging tile is free now)
@@ -654,43 +659,34 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         for (int j = jb + tid; j < jn; j += kTileThreads) {
           float gr = 0.f;
           for (int pg = 0; pg < groups; ++pg) gr += red[(size_t)pg * ncol * 4 + (j - jb)];
-          const int i = flat_index_of_gp(g, j);
-          if (i >= 0) {
-            if (dp) my_sym[i] = gr;
-            else adam_update(f, g, i, gr, s_step_size, s_inv_bc2_sqrt);
+          if (dp) {
+            // push my slot to every rank (remote 8-byte stores, coalesced per warp), then collect the world's slots
+            // for the same j from my own buffer and sum them in rank order (identical arithmetic on every rank).
+            const unsigned long long word = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(gr);
+            for (int r = 0; r < f.world; ++r)
+              *(reinterpret_cast<volatile unsigned long long*>(const_cast<float*>(f.peer_bufs[r])) + ll_src + j) = word;
+            float gsum = 0.f;
+            const volatile unsigned long long* mine =
+                reinterpret_cast<const volatile unsigned long long*>(f.peer_bufs[f.rank]) + (size_t)(epoch & 1) * f.world * nj + j;
+            const long long t0 = clock64();
+            for (int r = 0; r < f.world; ++r) {
+              unsigned long long w = mine[(size_t)r * nj];
+              while ((uint32_t)(w >> 32) != tag) {
+                if (clock64() - t0 > 6000000000LL) { atomicExch(&g_tc_status, 51); break; }
+                w = mine[(size_t)r * nj];
+              }
+              gsum += __uint_as_float((uint32_t)w);
+            }
+            const int i = flat_index_of_gp(g, j);
+            if (i >= 0) adam_update(f, g, i, gsum, s_step_size, s_inv_bc2_sqrt);
+          } else {
+            const int i = flat_index_of_gp(g, j);
+            if (i >= 0) adam_update(f, g, i, gr, s_step_size, s_inv_bc2_sqrt);
           }
         }
         __syncthreads();
       }
       B2H_STAMP();   // tail: reduction (+ Adam when single-GPU) done
-      if (dp) {
-        // gradient exchange over peer (NVLink) memory, protocol of adam_dp_kernel (b2h_optim.cu)
-        grid_barrier(f.sync, tid);                       // this rank's flat gradient is complete
-        const size_t flag_off = 2 * P;
-        if (blockIdx.x == 0 && tid < f.world) {
-          __threadfence_system();
-          volatile long long* fl = reinterpret_cast<volatile long long*>(const_cast<float*>(f.peer_bufs[tid]) + flag_off) + f.rank;
-          *fl = epoch;
-          __threadfence_system();
-        }
-        if (tid < f.world) {
-          const volatile long long* fl = reinterpret_cast<const volatile long long*>(f.peer_bufs[f.rank] + flag_off) + tid;
-          const long long t0 = clock64();
-          while (*fl < epoch) {
-            if (clock64() - t0 > 6000000000LL) { atomicExch(&g_tc_status, 51); break; }
-          }
-          __threadfence_system();
-        }
-        __syncthreads();
-        const int perp = round_up((g.P + nparts - 1) / nparts, 32);
-        const int i_end = min(g.P, (int)(blockIdx.x + 1) * perp);
-        const size_t off = (size_t)(epoch & 1) * P;
-        for (int i = blockIdx.x * perp + tid; i < i_end; i += kTileThreads) {
-          float gr = 0.f;
-          for (int r = 0; r < f.world; ++r) gr += __ldcv(f.peer_bufs[r] + off + i);
-          adam_update(f, g, i, gr, s_step_size, s_inv_bc2_sqrt);
-        }
-      }
     }
   }
   if (!TRAIN && tid == 0) bulk_wait0();

@@ -61,14 +61,13 @@ def broadcast_parameters(model: ConvModel, src: int = 0, group=None):
         model.mark_packed_stale()
 
 
-def _symmetric_exchange_buffer(n_params: int, device, group):
+def _symmetric_exchange_buffer(n_floats: int, device, group):
     """Peer-mapped buffer [2][P] fp32 gradients + [world] int64 flags on every rank (torch symmetric memory:
     cuMem allocations mapped into every peer over NVLink).  Returns (local tensor, device array of peer base
     pointers indexed by rank)."""
     import torch.distributed._symmetric_memory as symm_mem
     world = dist.get_world_size(group)
-    n = 2 * n_params + 2 * world + 8                     # flags are int64 = 2 floats each
-    buf = symm_mem.empty(n, dtype=torch.float32, device=device)
+    buf = symm_mem.empty(n_floats, dtype=torch.float32, device=device)
     buf.zero_()
     hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
     ptrs = [int(p) for p in hdl.buffer_ptrs]
@@ -121,7 +120,9 @@ class DataParallelTrainer:
         self.sym = self.sym_hdl = self.peer_ptrs = None
         if self.world > 1 and exchange in ("auto", "p2p"):
             try:
-                self.sym, self.sym_hdl, self.peer_ptrs = _symmetric_exchange_buffer(flat.numel(), dev, group)
+                n_in_, C_, pe_ = model._geometry()
+                nfl = int(self.lib.b2h_dp_exchange_floats(n_in_, C_, pe_, self.world))
+                self.sym, self.sym_hdl, self.peer_ptrs = _symmetric_exchange_buffer(nfl, dev, group)
                 self.epoch_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
                 self.rank = dist.get_rank(group)
                 self.exchange = "p2p"

@@ -160,6 +160,9 @@ int b2h_train_forward_backward_dp(const void* x, int x_dtype, const float* targe
 int b2h_adam_step_dp(float* params, const void* peer_bufs_dev, int rank, int world, float* exp_avg, float* exp_avg_sq,
                      int64_t n, double lr, double beta1, double beta2, double eps, const int64_t* step_dev,
                      const int64_t* epoch_dev, float grad_scale, void* packed, int n_in, int C, int pos_emb, void* stream);
+/* floats a rank's exchange buffer must hold for b2h_train_step_dp / b2h_adam_step_dp */
+int64_t b2h_dp_exchange_floats(int n_in, int C, int pos_emb, int world);
+
 /* The whole data-parallel step as ONE call; in bf16 mode (tensor-core tile kernel) also ONE cooperative kernel
  * launch per rank: forward + loss + backward, grid barrier, cross-CTA reduction into the exchange buffer, flag
  * exchange + gradient sum over peer memory, Adam + re-pack.  Other shapes run the same protocol as three launches. */

@@ -42,6 +42,15 @@ if os.environ.get("B2H_DIAG_GRAPH", "1") == "1":
         tr.replay()
     torch.cuda.synchronize(); say("graph steps", (time.time() - t0) / 100 * 1e6, "us/step")
 from hand_pose_sl_b200 import _lib
+lib = _lib.load()
+buf = torch.zeros(128, dtype=torch.int64, device=dev)
+for rep in range(2):
+    torch.cuda.synchronize(); dist.barrier()
+    buf.zero_(); lib.b2h_debug_timing(_lib.ptr(buf))
+    tr.step(0); torch.cuda.synchronize()
+    lib.b2h_debug_timing(None)
+    st = [int(v) for v in buf.cpu().tolist() if v != 0]
+    say("stamps", len(st), "total", st[-1] - st[0], "tail deltas", [st[i + 1] - st[i] for i in range(len(st) - 8, len(st) - 1)])
 say("dp_status", _lib.load().b2h_dp_status(), "loss", float(tr.loss[0]))
 dist.barrier(); say("done")
 sys.stdout.flush(); os._exit(0)
