@@ -292,7 +292,9 @@ def main():
             kgraph.replay()
         ev1.record()
         torch.cuda.synchronize()
-        k_ms = ev0.elapsed_time(ev1) / reps
+        k_only_ms = ev0.elapsed_time(ev1) / reps            # forward+loss+backward kernel without the fused tail
+        fused = launches_per_step == 1                      # bf16 mode: the whole step IS one kernel launch
+        k_ms = (ms / args.steps) if fused else k_only_ms
         tfl = TRAIN_FLOP_PER_WINDOW * B_TRAIN / (k_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -300,9 +302,9 @@ def main():
             traffic = json.load(open(tpath)).get("train_kernel_dram_bytes_per_launch")
         line["roofline"] = {"bound": "tensor", "achieved": tfl, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tfl / pk["tflops"],
                             "traffic": traffic, "kernel": "conv_fp32_kernel<train>" if train_prec == "fp32" else "conv_tc_tile_kernel<train>",
-                            "kernel_ms": k_ms, "algorithmic_flop_per_launch": TRAIN_FLOP_PER_WINDOW * B_TRAIN,
+                            "kernel_ms": k_ms, "kernel_ms_fwd_bwd_only": k_only_ms, "algorithmic_flop_per_launch": TRAIN_FLOP_PER_WINDOW * B_TRAIN,
                             "peak_source": pk["source"] + ", bf16 dense sustained",
-                            "note": "CUDA-graph replay of the kernel alone over the rotating batches (inter-kernel gaps included); per-launch device time is in profiles/"}
+                            "note": "bf16 mode: one cooperative launch per step (fwd+loss+bwd, grid barrier, reduction, Adam), timed over the graph-replayed steps (inter-kernel gaps included); kernel_ms_fwd_bwd_only = the same kernel without its reduction/Adam tail; per-launch device times are in profiles/"}
 
         if not args.skip_extras:
             # ---------------- config 2: forward, batch 512 x 64, bf16 tensor-core path ----------------
@@ -355,10 +357,14 @@ def main():
             torch.cuda.synchronize()
             p_ms = ev0.elapsed_time(ev1) / preps
             gbs = F * PRE_BYTES_PER_FRAME / (p_ms * 1e-3) / 1e9
+            ptraffic = None
+            if os.path.isfile(tpath):
+                pf = json.load(open(tpath)).get("preprocess_dram_bytes_per_frame")
+                ptraffic = pf * F if pf else None
             line["preprocess"] = {"metric": "body2hand_preprocess_frames_per_sec", "value": F / (p_ms * 1e-3), "unit": "frames/s",
                                   "ms_per_launch": p_ms, "workload": f"{F} frames (2 h at 30 fps), full reference item (1452 B/frame)",
                                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                               "frac": gbs / pk["hbm_gbs"], "traffic": None,
+                                               "frac": gbs / pk["hbm_gbs"], "traffic": ptraffic,
                                                "note": "CUDA-graph replay, outputs reused; 314 MB moved per launch > 126 MB L2"}}
         # ---------------- CPU baseline (reference path on this box's host cores) ----------------
         line["cpu_baseline"], _, _ = cpu_reference_arm(200, 2, budget_s=15.0)
