@@ -50,7 +50,7 @@ struct TcTileArgs {
   Geo geo;
 };
 
-constexpr int kTileThreads = 128;
+constexpr int kTileThreads = 256;   // 8 warps: two per TMEM lane quadrant (each takes every other 16-column chunk)
 constexpr int kAccCol = 0;        // forward / dgrad accumulator: columns [0, 64)
 constexpr int kWgCol = 64;        // weight-gradient accumulators: 2 layer pairs x (5 taps x 32 + 8 bias) columns
 constexpr int kWgPairCols = 5 * 32 + 8;
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   __shared__ __align__(8) uint64_t tbar;     // target tile landed (train)
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float bias_s[4][64];
-  __shared__ float red_s[4];
+  __shared__ float red_s[8];
   const Geo& g = p.geo;
   const int T = p.T, MB = p.MB, HR = p.HR, nhalf = p.nhalf, gh = p.gh;
   const int tid = threadIdx.x, lane = tid & 31;
@@ -181,12 +181,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   float* YS = reinterpret_cast<float*>(smem + L.ys);
   B2H_STAMP();   // kernel start
 
-  // this thread's row: TMEM lane == tid
-  const int hh = (nhalf == 2) ? ((tid >> 4) & 1) : 0;
-  const int m = (nhalf == 2) ? ((tid >> 5) * 16 + (tid & 15)) : tid;
+  // this thread's row: TMEM lane == tid & 127 (warps w and w+4 share lane quadrant w & 3 and split the columns)
+  const int r128 = tid & 127;
+  const int ch = warp >> 2;                      // column half: chunks c0 = 16*ch, 16*ch + 32, ...
+  const int hh = (nhalf == 2) ? ((r128 >> 4) & 1) : 0;
+  const int m = (nhalf == 2) ? ((r128 >> 5) * 16 + (r128 & 15)) : r128;
   const int row = hh * HR + 2 + m;
   const int wj = m / (T + 2), t = m - wj * (T + 2);
-  const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
   const int srow = hh * MB + m;                  // row of this thread in the fp32 staging tile
   const bool bulk_io = (T & 1) == 0;             // T*168 B and the staging row offsets are 16-B multiples
   const int wpt = nhalf * gh;                    // windows per tile
@@ -207,12 +209,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + ((size_t)gw * T + t) * n_in);
 #pragma unroll
       for (int c = 0; c < 8; ++c)
-        if (c < 2 * cpr) xf[c] = __ldg(src + c);
+        if (c < 2 * cpr && ((c >> 1) & 1) == ch) xf[c] = __ldg(src + c);
     } else {
       const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + ((size_t)gw * T + t) * n_in);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        if (c < cpr) xb[c] = __ldg(src + c);
+        if (c < cpr && (c & 1) == ch) xb[c] = __ldg(src + c);
     }
   };
   prefetch_x(blockIdx.x);
@@ -267,28 +269,32 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   auto readout_pair = [&](int pr) {
     float* part = p.partials + (size_t)blockIdx.x * gp_total(g);
     const int l = 2 * pr + (lane >> 4);
-    const int co = warp * 16 + (lane & 15);
+    const int co = (warp & 3) * 16 + (lane & 15);
     const bool mine = co < g.cout[l];
     const int Nw = g.kp[l];
     float* lp = part + gp_layer_off(g, l);
     const uint32_t dcol = tbase + lane_addr + kWgCol + pr * kWgPairCols;
-    uint32_t v[B2H_KW][32];
+    // column half 0 reads taps 0..2, half 1 taps 3..4 and the bias column
+    const int k0 = ch == 0 ? 0 : 3, nk = ch == 0 ? 3 : 2;
+    uint32_t v[3][32];
 #pragma unroll
-    for (int k = 0; k < B2H_KW; ++k) tmem_ld32(dcol + k * 32, v[k]);
+    for (int k = 0; k < 3; ++k)
+      if (k < nk) tmem_ld32(dcol + (k0 + k) * 32, v[k]);
     uint32_t vb[16];
-    tmem_ld16(dcol + 5 * 32, vb);      // 8 valid columns; column 0 holds db (ones sits in element 0)
+    if (ch == 1) tmem_ld16(dcol + 5 * 32, vb);      // 8 valid columns; column 0 holds db (ones sits in element 0)
     tmem_ld_wait();
     if (mine) {
 #pragma unroll
-      for (int k = 0; k < B2H_KW; ++k) {
-        float4* dst = reinterpret_cast<float4*>(lp + ((size_t)k * g.cout[l] + co) * Nw);
+      for (int k = 0; k < 3; ++k) {
+        if (k >= nk) continue;
+        float4* dst = reinterpret_cast<float4*>(lp + ((size_t)(k0 + k) * g.cout[l] + co) * Nw);
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           if (q * 4 < Nw)
             dst[q] = make_float4(__uint_as_float(v[k][4 * q]), __uint_as_float(v[k][4 * q + 1]), __uint_as_float(v[k][4 * q + 2]),
                                  __uint_as_float(v[k][4 * q + 3]));
       }
-      lp[B2H_KW * g.cout[l] * Nw + co] = __uint_as_float(vb[0]);
+      if (ch == 1) lp[B2H_KW * g.cout[l] * Nw + co] = __uint_as_float(vb[0]);
     }
   };
 
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         if (p.x_dtype == B2H_DT_F32) {
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8)
-            if (c8 < cpr) {
+            if (c8 < cpr && (c8 & 1) == ch) {
               const float4 lo = xf[2 * c8], hi = xf[2 * c8 + 1];
               const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
               store8_bf16(X, CH, row, c8, v);
@@ -329,10 +335,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         } else {
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8)
-            if (c8 < cpr) *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = xb[c8];
+            if (c8 < cpr && (c8 & 1) == ch) *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = xb[c8];
         }
       } else if (valid) {
-        for (int c8 = 0; c8 < nch0; ++c8) {
+        for (int c8 = ch; c8 < nch0; c8 += 2) {
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -350,9 +356,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         }
       } else {
         const uint4 zero = make_uint4(0, 0, 0, 0);
-        for (int c8 = 0; c8 < nch0; ++c8) *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = zero;
+        for (int c8 = ch; c8 < nch0; c8 += 2) *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = zero;
       }
-      if (TRAIN) {   // ones column (B operand of the bias-gradient GEMM): 1 on real frames
+      if (TRAIN && ch == 0) {   // ones column (B operand of the bias-gradient GEMM): 1 on real frames
         uint4 o = make_uint4(0, 0, 0, 0);
         if (valid) o.x = 0x00003F80u;             // bf16(1.0) in element 0
         *reinterpret_cast<uint4*>(ONES + (size_t)row * 16) = o;
@@ -390,7 +396,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       B2H_STAMP();   // fwd layer: accumulator ready
       const uint32_t taddr = tbase + lane_addr + kAccCol;
       if (l < 3) {
-        for (int c0 = 0; c0 < N; c0 += 16) {
+        for (int c0 = 16 * ch; c0 < N; c0 += 32) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         if (tgt_smem) { mbar_wait(&tbar, tphase, 18); tphase ^= 1; }
         B2H_STAMP();   // layer-4 epilogue: target tile landed
         float sum = 0.f;
-        for (int c0 = 0; c0 < N; c0 += 16) {
+        for (int c0 = 16 * ch; c0 < N; c0 += 32) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
@@ -500,7 +506,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       }
       B2H_STAMP();   // fwd layer: epilogue done
     }
-    if (TRAIN && p.mode == 1 && tid == 0) loss_acc += red_s[0] + red_s[1] + red_s[2] + red_s[3];
+    if (TRAIN && p.mode == 1 && tid == 0) loss_acc += ((red_s[0] + red_s[1]) + (red_s[2] + red_s[3])) + ((red_s[4] + red_s[5]) + (red_s[6] + red_s[7]));
 
     if (TRAIN) {
       // =========================== backward ===========================
@@ -553,7 +559,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           // dZ_{l-1} = dA_{l-1} * (a_{l-1} > 0)     (ReLU backward on the saved activation)
           const int Nd = round_up(g.cin[l], 16);
           const uint32_t taddr = tbase + lane_addr + kAccCol;
-          for (int c0 = 0; c0 < Nd; c0 += 16) {
+          for (int c0 = 16 * ch; c0 < Nd; c0 += 32) {
             uint32_t v[16];
             tmem_ld16(taddr + c0, v);
             tmem_ld_wait();
@@ -606,7 +612,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         s_step_size = (float)(f.lr / (1.0 - pow(f.beta1, tt)));
         s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(f.beta2, tt)));
       }
-      if (blockIdx.x == 0 && warp == 1 && f.loss_out) {  // loss = sum of the CTAs' loss partials (fixed order)
+      if (blockIdx.x == 0 && warp == 7 && f.loss_out) {  // loss = sum of the CTAs' loss partials (fixed order)
         float sl = 0.f;
         for (int c = lane; c < (int)gridDim.x; c += 32) sl += __ldcg(p.loss_partials + c);
 #pragma unroll
