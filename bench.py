@@ -366,6 +366,36 @@ def main():
                                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                                "frac": gbs / pk["hbm_gbs"], "traffic": ptraffic,
                                                "note": "CUDA-graph replay, outputs reused; 314 MB moved per launch > 126 MB L2"}}
+        if not args.skip_extras:
+            # ---------------- config 5: streaming K0 -> K1 over 1 h of frames (stride 64 and 16) ----------------
+            Fs = 108000
+            sp_, sl_, sr_ = (t_[:Fs].contiguous() for t_ in (tp, tl, tr))
+            pre_s = b2h.PreprocessRightHand(with_left_hand=False, emit_bf16=(fwd_prec == "bf16"))
+            line["stream"] = {"workload": f"{Fs} frames (1 h at 30 fps): K0 preprocessing (+bf16 copy) -> forward over 64-frame windows, CUDA graph",
+                              "dtype": fwd_prec}
+            for stride in (64, 16):
+                st_ = torch.from_numpy(b2h.sliding_window_starts(Fs - T + 1, T, stride)).to(dev)
+                Wn = st_.numel()
+                so = pre_s(sp_, sl_, sr_, st_, T)
+                xin = so["input_kp_bf16"] if fwd_prec == "bf16" else so["input_kp"]
+                frs = ForwardRunner(fmodel, Wn, T, n_slots=1, x_dtype=xin.dtype, out_scale=1280.0)
+                frs.x = xin.view(1, Wn, T, 12, 2)              # the net reads K0's output in place (no copy)
+                pre_s(sp_, sl_, sr_, st_, T, out=so); frs.run(0)
+                torch.cuda.synchronize()
+                sg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(sg):
+                    for _ in range(4):
+                        pre_s(sp_, sl_, sr_, st_, T, out=so)
+                        frs.run(0)
+                sg.replay(); torch.cuda.synchronize()
+                ev0.record()
+                for _ in range(5):
+                    sg.replay()
+                ev1.record()
+                torch.cuda.synchronize()
+                s_ms = ev0.elapsed_time(ev1) / 20
+                line["stream"][f"stride{stride}"] = {"windows": Wn, "ms": s_ms, "unique_frames_per_sec": Fs / (s_ms * 1e-3),
+                                                     "window_frames_per_sec": Wn * T / (s_ms * 1e-3)}
         # ---------------- CPU baseline (reference path on this box's host cores) ----------------
         line["cpu_baseline"], _, _ = cpu_reference_arm(200, 2, budget_s=15.0)
 

@@ -105,3 +105,23 @@ def test_errors_mirror_reference():
     mp = b2h.ConvModel(30, "ReLU", True).to(DEV)
     with pytest.raises(RuntimeError):                       # pos_emb only works for T == 100 (HandPoseModels.py:82)
         mp(torch.zeros(1, 64, 12, 2, device=DEV))
+
+
+@pytest.mark.parametrize("stride", [64, 16])
+def test_streaming_pipeline_k0_to_k1(stride):
+    """BASELINE config 5: raw OpenPose clip -> K0 (bit-exact preprocessing, bf16 copy for the net) -> K1 forward over
+    sliding windows, against the oracle pipeline (reference transforms + reference ConvModel) on the same clip."""
+    F, T = 1000, 64
+    pose, lh, rh = synthetic.synthetic_clip(F, seed=21)
+    starts = b2h.sliding_window_starts(F, T, stride)
+    want_item = oracle.preprocess_windows(pose, lh, rh, starts, T)
+    sd = oracle.init_params(30, False, seed=0)
+    ref = oracle.conv_model_forward(sd, torch.from_numpy(want_item["input_kp"])).contiguous().numpy() * np.float32(1280)
+    pre = b2h.PreprocessRightHand(emit_bf16=True)
+    out = pre(torch.from_numpy(pose).to(DEV), torch.from_numpy(lh).to(DEV), torch.from_numpy(rh).to(DEV), starts, T)
+    assert np.array_equal(out["input_kp"].cpu().numpy(), want_item["input_kp"])          # K0 stays bit-exact
+    for prec, x in (("bf16", out["input_kp_bf16"]), ("fp32", out["input_kp"])):
+        m = _model(sd, 30, False, prec)
+        y = m.predict(x, denormalize=1280)                                                 # traintest.py:270-271
+        _tc_clean()
+        assert oracle.rel_err(y.cpu().numpy(), ref) <= TOL[prec]
