@@ -341,6 +341,43 @@ def validate_batch(sd, input_kp, target_kp, lengths, loss_kind="L1", target_conf
     return float(poderated_pose_l1(prediction, target_kp, lengths, target_conf))
 
 
+def train_grads_bf16_emulated(sd, input_kp, target_kp, lengths, loss_kind="L1", target_conf=None):
+    """What an IDEAL bf16-operand / fp32-accumulate implementation of traintest.py:94-120 computes: the reference
+    formulas with every GEMM operand rounded to bf16 (weights, input, post-ReLU activations, dY, dZ) and everything
+    else (accumulation, bias, loss, sign) in fp32.  Used to separate kernel bugs from bf16 rounding: the tensor-core
+    kernels must match THIS closely, and this matches the fp32 reference within the bf16 tolerances."""
+    bf = lambda t: t.to(torch.bfloat16).float()
+    B, T = input_kp.shape[:2]
+    ln = torch.as_tensor(lengths, dtype=torch.int64)
+    a = [bf(input_kp.reshape(B, T, -1).permute(0, 2, 1))]
+    W = [bf(sd[f"conv{i}.weight"]) for i in range(1, 5)]
+    b = [sd[f"conv{i}.bias"] for i in range(1, 5)]
+    for l in range(3):
+        a.append(bf(F.relu(F.conv1d(a[-1], W[l], b[l], padding=2))))
+    pred = F.conv1d(a[-1], W[3], b[3], padding=2)                               # (B,42,T) fp32
+    mask = (torch.arange(T)[None, :] < ln[:, None]).float()[:, None, :]
+    pred = pred * mask                                                           # mask_output  utils.py:309-312
+    t42 = target_kp.reshape(B, T, 42).permute(0, 2, 1)
+    n_el = (ln.float() * 42)[:, None, None]
+    if loss_kind == "L1":
+        d = pred - t42
+        loss = ((d.abs() * mask).sum(dim=(1, 2)) / n_el[:, 0, 0]).sum() / B
+        dy = torch.sign(d) * mask / (B * n_el)
+    else:
+        s = target_conf.permute(0, 2, 1).repeat_interleave(2, dim=1)
+        d = pred * s - t42 * s
+        loss = ((d.abs() * mask).sum(dim=(1, 2)) / n_el[:, 0, 0]).sum()
+        dy = torch.sign(d) * s * mask / n_el
+    grads = {}
+    dz = bf(dy)
+    for l in (3, 2, 1, 0):
+        grads[f"conv{l + 1}.weight"] = torch.nn.grad.conv1d_weight(a[l], W[l].shape, dz, padding=2)
+        grads[f"conv{l + 1}.bias"] = dz.sum(dim=(0, 2))
+        if l > 0:
+            dz = bf(torch.nn.grad.conv1d_input(a[l].shape, W[l], dz, padding=2) * (a[l] > 0).float())
+    return float(loss), grads, pred.permute(0, 2, 1).reshape(B, T, 21, 2)
+
+
 def adam_reference_step(p, g, m, v, step, lr=2e-4, b1=0.9, b2=0.999, eps=1e-8):
     """torch.optim.Adam single-tensor update (defaults of traintest.py:48), written out; float64 in,
     used to cross-check the fused CUDA Adam independent of torch's foreach implementation."""
