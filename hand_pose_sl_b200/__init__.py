@@ -6,8 +6,10 @@ from . import _lib, synthetic  # noqa: F401
 from .models import ConvModel, LinearPositionalEmbedding  # noqa: F401
 from .steps import (FusedAdam, L12Pixels, adjust_learning_rate, forward_backward, fused_train_step,  # noqa: F401
                     mask_output, maskedPoseL1, poderatedPoseL1, validate_batch)
+from .datasets import GpuPoseDataset, PackedClips, pack_metadata, split_metadata  # noqa: F401
 from .transforms import BODY_HEAD_KEYPOINTS, PreprocessRightHand, select_window, sliding_window_starts  # noqa: F401
 
 __all__ = ["ConvModel", "LinearPositionalEmbedding", "maskedPoseL1", "poderatedPoseL1", "mask_output", "FusedAdam",
            "fused_train_step", "forward_backward", "validate_batch", "PreprocessRightHand", "select_window",
-           "sliding_window_starts", "L12Pixels", "adjust_learning_rate", "BODY_HEAD_KEYPOINTS"]
+           "sliding_window_starts", "L12Pixels", "adjust_learning_rate", "BODY_HEAD_KEYPOINTS", "GpuPoseDataset", "PackedClips",
+           "pack_metadata", "split_metadata"]

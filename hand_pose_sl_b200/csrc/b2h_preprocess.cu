@@ -58,6 +58,7 @@ struct PreArgs {
   const float* src[3];
   int64_t n_frames;
   const int64_t* win_start;
+  const int64_t* win_end;   // nullable: exclusive end of the clip each window is cropped from (default n_frames)
   int n_win, T, pad_mode, dif, normalize, aligned, fastdiv;
   float factor, rfactor;
   float* out[6];  // input_kp, input_conf, target_kp, target_conf, left_kp, left_conf
@@ -230,12 +231,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) preprocess_kernel(PreA
     for (int i = 0; i < 4; ++i) {
       if (s0 + i < S) {
         const int64_t start = p.win_start[w];
+        int64_t cend = p.win_end ? p.win_end[w] : p.n_frames;      // end of the utterance this window belongs to
+        cend = cend > p.n_frames ? p.n_frames : cend;
         int64_t f = start + t;                        // crop [start, start+T)   text_pose_dataset.py:66-68
-        if (f >= p.n_frames || f < 0)                 // past the clip end -> pad rule
-          f = (p.pad_mode == B2H_PAD_REPEAT_FIRST && start >= 0 && start < p.n_frames) ? start : -1;  // :512-518 / :616-622
+        if (f >= cend || f < 0)                       // past the clip end -> pad rule
+          f = (p.pad_mode == B2H_PAD_REPEAT_FIRST && start >= 0 && start < cend) ? start : -1;  // :512-518 / :616-622
         srcf[i] = f;
         if (t == 0 && lane == 0 && p.n_frames_out) {
-          const int64_t rem = p.n_frames - start;
+          const int64_t rem = cend - start;
           p.n_frames_out[w] = rem < 0 ? 0 : (rem < p.T ? rem : (int64_t)p.T);   // :447
         }
       } else {
@@ -377,7 +380,7 @@ extern "C" int b2h_verify_fastdiv(float factor, unsigned long long* mismatches_d
 }
 
 extern "C" int b2h_preprocess(const float* pose25, const float* hand_left, const float* hand_right, int64_t n_frames,
-                              const int64_t* win_start, int n_win, int T, int pad_mode, float factor,
+                              const int64_t* win_start, const int64_t* win_end, int n_win, int T, int pad_mode, float factor,
                               int dif_encoding, int normalize, float* input_kp, float* input_conf,
                               float* target_kp, float* target_conf, float* left_kp, float* left_conf,
                               int64_t* n_frames_out, void* input_kp_bf16, void* stream) {
@@ -389,7 +392,7 @@ extern "C" int b2h_preprocess(const float* pose25, const float* hand_left, const
   if (n_frames < 0 || n_win < 0 || T < 0) { set_error("b2h_preprocess: negative size"); return B2H_ESHAPE; }
   PreArgs p{};
   p.src[0] = pose25; p.src[1] = hand_left; p.src[2] = hand_right;
-  p.n_frames = n_frames; p.win_start = win_start; p.n_win = n_win; p.T = T; p.pad_mode = pad_mode;
+  p.n_frames = n_frames; p.win_start = win_start; p.win_end = win_end; p.n_win = n_win; p.T = T; p.pad_mode = pad_mode;
   p.dif = dif_encoding; p.normalize = normalize; p.factor = factor;
   p.rfactor = 1.0f / factor; p.fastdiv = (factor == 1280.0f) ? 1 : 0;   // the reference's factor (run.py:90): verified exhaustively
   p.out[0] = input_kp; p.out[1] = input_conf; p.out[2] = target_kp; p.out[3] = target_conf;
@@ -402,7 +405,8 @@ extern "C" int b2h_preprocess(const float* pose25, const float* hand_left, const
   return launch_pre<0>(p, (cudaStream_t)stream);
 }
 
-extern "C" int b2h_preprocess_h5(const float* rows150, int64_t n_frames, const int64_t* win_start, int n_win, int T,
+extern "C" int b2h_preprocess_h5(const float* rows150, int64_t n_frames, const int64_t* win_start, const int64_t* win_end,
+                                 int n_win, int T,
                                  int pad_mode, float factor, int dif_encoding, int normalize, float* input_kp,
                                  float* input_conf, float* target_kp, float* target_conf, float* left_kp,
                                  float* left_conf, int64_t* n_frames_out, void* stream) {
@@ -414,7 +418,7 @@ extern "C" int b2h_preprocess_h5(const float* rows150, int64_t n_frames, const i
   if (n_frames < 0 || n_win < 0 || T < 0) { set_error("b2h_preprocess_h5: negative size"); return B2H_ESHAPE; }
   PreArgs p{};
   p.src[0] = rows150; p.src[1] = nullptr; p.src[2] = nullptr;
-  p.n_frames = n_frames; p.win_start = win_start; p.n_win = n_win; p.T = T; p.pad_mode = pad_mode;
+  p.n_frames = n_frames; p.win_start = win_start; p.win_end = win_end; p.n_win = n_win; p.T = T; p.pad_mode = pad_mode;
   p.dif = dif_encoding; p.normalize = normalize; p.factor = factor;
   p.rfactor = 1.0f / factor; p.fastdiv = (factor == 1280.0f) ? 1 : 0;   // the reference's factor (run.py:90): verified exhaustively
   p.out[0] = input_kp; p.out[1] = input_conf; p.out[2] = target_kp; p.out[3] = target_conf;

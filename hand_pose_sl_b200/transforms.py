@@ -56,9 +56,9 @@ class PreprocessRightHand:
         out["right_hand_kp"], out["right_hand_conf"] = out["target_kp"], out["target_conf"]
         return out
 
-    def __call__(self, pose25, hand_left, hand_right, win_start, T, out=None):
+    def __call__(self, pose25, hand_left, hand_right, win_start, T, out=None, win_end=None):
         """pose25 (F,25,3), hand_left/right (F,21,3) fp32 CUDA tensors (OpenPose [x,y,c]); win_start (W,)
-        int64; `out` = the dict returned by an earlier call with the same (W, T) to reuse its buffers; returns the stacked item dict: input_kp (W,T,12,2), input_conf (W,T,12), target_kp
+        int64; `win_end` (W,) optional exclusive end of the utterance each window is cropped from; `out` = the dict returned by an earlier call with the same (W, T) to reuse its buffers; returns the stacked item dict: input_kp (W,T,12,2), input_conf (W,T,12), target_kp
         (W,T,21,2), target_conf (W,T,21), left_hand_*, n_frames (W,) int64 (device)."""
         _lib.require_device(pose25, "pose25")
         _lib.require_sm100(pose25.device)
@@ -68,14 +68,17 @@ class PreprocessRightHand:
             raise RuntimeError("expected pose25 (F,25,3), hand_left (F,21,3), hand_right (F,21,3)")
         pose25, hand_left, hand_right = (_dev_f32(a, dev) for a in (pose25, hand_left, hand_right))
         ws = torch.as_tensor(win_start).to(device=dev, dtype=torch.int64).contiguous()
+        we = None if win_end is None else torch.as_tensor(win_end).to(device=dev, dtype=torch.int64).contiguous()
         W = ws.numel()
+        if we is not None and we.numel() != W:
+            raise RuntimeError("win_end must have one entry per window")
         if out is None:
             out = self._outputs(W, T, 12, dev)
             bf = torch.empty((W, T, 24), dtype=torch.bfloat16, device=dev) if self.emit_bf16 else None
         else:      # caller-owned output dict of a previous call with the same (W, T): steady-state loops, CUDA graphs
             bf = out["input_kp_bf16"].view(W, T, 24) if self.emit_bf16 else None
         lib = _lib.load()
-        _lib.check(lib.b2h_preprocess(_lib.ptr(pose25), _lib.ptr(hand_left), _lib.ptr(hand_right), F, _lib.ptr(ws), W, T,
+        _lib.check(lib.b2h_preprocess(_lib.ptr(pose25), _lib.ptr(hand_left), _lib.ptr(hand_right), F, _lib.ptr(ws), _lib.ptr(we), W, T,
                                       self.pad_mode, self.factor, int(self.dif_encoding), int(self.normalize),
                                       _lib.ptr(out["input_kp"]), _lib.ptr(out["input_conf"]), _lib.ptr(out["target_kp"]),
                                       _lib.ptr(out["target_conf"]), _lib.ptr(out.get("left_hand_kp")),
@@ -85,7 +88,7 @@ class PreprocessRightHand:
             out["input_kp_bf16"] = bf.view(W, T, 12, 2)
         return self._alias(out)
 
-    def from_h5_rows(self, rows150, win_start, T):
+    def from_h5_rows(self, rows150, win_start, T, win_end=None):
         """Packed rows of TextPoseH5Dataset.array2item (text_pose_dataset.py:587-612): (F,150) =
         [x0..x49|y0..y49|c0..c49]; body = 8 keypoints."""
         _lib.require_device(rows150, "rows150")
@@ -96,10 +99,11 @@ class PreprocessRightHand:
         rows150 = _dev_f32(rows150, dev)
         F = rows150.shape[0]
         ws = torch.as_tensor(win_start).to(device=dev, dtype=torch.int64).contiguous()
+        we = None if win_end is None else torch.as_tensor(win_end).to(device=dev, dtype=torch.int64).contiguous()
         W = ws.numel()
         out = self._outputs(W, T, 8, dev)
         lib = _lib.load()
-        _lib.check(lib.b2h_preprocess_h5(_lib.ptr(rows150), F, _lib.ptr(ws), W, T, self.pad_mode, self.factor,
+        _lib.check(lib.b2h_preprocess_h5(_lib.ptr(rows150), F, _lib.ptr(ws), _lib.ptr(we), W, T, self.pad_mode, self.factor,
                                          int(self.dif_encoding), int(self.normalize), _lib.ptr(out["input_kp"]),
                                          _lib.ptr(out["input_conf"]), _lib.ptr(out["target_kp"]),
                                          _lib.ptr(out["target_conf"]), _lib.ptr(out.get("left_hand_kp")),

@@ -72,12 +72,13 @@ int b2h_pack_weights(const float* params, void* packed, int n_in, int C, int pos
  * WristDifference / ChestDifference / NormalizeFixedFactor / BuildRightHandItem
  * (steps/utils.py:180-210, 261-277).  Bit-exact (IEEE sub.rn then div.rn).
  * Inputs: OpenPose rows [x,y,c]: pose25 (F,25,3), hand_left (F,21,3), hand_right (F,21,3) fp32.
- * Window w covers source frames [win_start[w], win_start[w]+T) cut at F, padded by `pad_mode`.
+ * Window w covers source frames [win_start[w], win_start[w]+T) cut at win_end[w] (nullable: F) -- the end of the
+ * utterance it is cropped from when several utterances are packed back to back -- and padded by `pad_mode`.
  * Outputs (W,T,12,2) (W,T,12) (W,T,21,2) (W,T,21) [(W,T,21,2) (W,T,21) nullable] fp32,
  * n_frames_out (W) int64 = min(F - start, T)  (…:447);  input_kp_bf16 nullable (W,T,24) bf16 copy
  * feeding the bf16 net without a second pass. */
 int b2h_preprocess(const float* pose25, const float* hand_left, const float* hand_right, int64_t n_frames,
-                   const int64_t* win_start, int n_win, int T, int pad_mode, float factor, int dif_encoding,
+                   const int64_t* win_start, const int64_t* win_end, int n_win, int T, int pad_mode, float factor, int dif_encoding,
                    int normalize, float* input_kp, float* input_conf, float* target_kp, float* target_conf,
                    float* left_kp, float* left_conf, int64_t* n_frames_out, void* input_kp_bf16, void* stream);
 
@@ -89,7 +90,7 @@ int b2h_verify_fastdiv(float factor, unsigned long long* mismatches_dev, void* s
 /* Same for the packed H5 row format of TextPoseH5Dataset.array2item
  * (dataloaders/text_pose_dataset.py:587-612): rows (F,150) = [x0..x49 | y0..y49 | c0..c49],
  * body = columns 0..7 (8 keypoints), left hand 8..28, right hand 29..49.  Outputs (W,T,8,2) (W,T,8) ... */
-int b2h_preprocess_h5(const float* rows150, int64_t n_frames, const int64_t* win_start, int n_win, int T,
+int b2h_preprocess_h5(const float* rows150, int64_t n_frames, const int64_t* win_start, const int64_t* win_end, int n_win, int T,
                       int pad_mode, float factor, int dif_encoding, int normalize, float* input_kp,
                       float* input_conf, float* target_kp, float* target_conf, float* left_kp, float* left_conf,
                       int64_t* n_frames_out, void* stream);

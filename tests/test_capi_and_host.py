@@ -52,8 +52,8 @@ def test_null_and_bad_arguments_return_error_codes():
     lib = _lib.load()
     assert lib.b2h_conv_forward(None, 0, None, None, None, None, 1, 64, 24, 30, 0, 0, 0, 1.0, None) == -1
     assert "null pointer" in _lib.last_error()
-    assert lib.b2h_preprocess(None, None, None, 0, None, 0, 64, 0, 1280.0, 1, 1, None, None, None, None, None, None, None,
-                              None, None) == -1
+    assert lib.b2h_preprocess(None, None, None, 0, None, None, 0, 64, 0, 1280.0, 1, 1, None, None, None, None, None, None,
+                              None, None, None) == -1
     assert lib.b2h_pack_weights(None, None, 24, 30, 0, None) == -1
     assert lib.b2h_adam_step(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 1, None, 1.0, None, 0, 0, 0, None) == -1
 
