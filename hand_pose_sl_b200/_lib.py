@@ -63,6 +63,7 @@ _SIGNATURES = {
                                   c_void_p]),
     "b2h_dp_exchange_floats": (c_int64, [c_int, c_int, c_int, c_int]),
     "b2h_dp_status": (c_int, []),
+    "b2h_format_prediction": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "b2h_tc_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b2h_tc_status": (c_int, []),
     "b2h_debug_timing": (None, [c_void_p]),

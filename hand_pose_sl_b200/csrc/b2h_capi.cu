@@ -325,6 +325,12 @@ extern "C" int b2h_pose_l1(const float* pred, const float* target, const float* 
   return launch_pose_l1(pred, target, scores, lengths, B, T, row_elems, loss_kind, loss_out, d_pred, row_scratch, (cudaStream_t)stream);
 }
 
+extern "C" int b2h_format_prediction(const float* pred, float* out, int64_t rows, int mode, void* stream) {
+  if (!pred || !out) { set_error("b2h_format_prediction: null pointer"); return B2H_EINVAL; }
+  if (rows < 0 || (mode != 0 && mode != 1)) { set_error("b2h_format_prediction: bad rows/mode"); return B2H_EINVAL; }
+  return launch_format_prediction(pred, out, rows, mode, (cudaStream_t)stream);
+}
+
 extern "C" int b2h_tc_probe(const void* a_bf16, const void* b_bf16, float* out, int n, int ksteps, int shift, int variant,
                             void* stream) {
   if (!a_bf16 || !b_bf16 || !out) { set_error("b2h_tc_probe: null pointer"); return B2H_EINVAL; }

@@ -198,6 +198,7 @@ int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream);
 
 void set_debug_timing(long long* p);
 int launch_tc_bench(long long* out, int M, int N, int reps, int nacc, int mn_major, cudaStream_t stream);
+int launch_format_prediction(const float* pred, float* out, int64_t rows, int mode, cudaStream_t stream);
 int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t stream);
 int launch_reduce(const float* partials, int nparts, int gp_layout, const Geo& g, float* grads, const float* loss_partials,
                   float* loss_out, cudaStream_t stream, const long long* epoch_dev = nullptr);

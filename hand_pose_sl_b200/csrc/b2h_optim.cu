@@ -263,6 +263,35 @@ __global__ void pose_l1_final_kernel(const float* __restrict__ row_scratch, int 
   }
 }
 
+// Inference output formats.  pred (R,42) = rows of [x0,y0,x1,y1,...] ->
+//   mode 0: OpenPose hand rows [x0,y0,1.0, x1,y1,1.0, ...] (63)      array2open_pose        steps/utils.py:355-364
+//   mode 1: packed H5 rows     [x0..x20 | y0..y20 | 0 x 21]  (63)      order_and_reshape_toh5 steps/traintest.py:302-317
+__global__ void format_prediction_kernel(const float* __restrict__ pred, float* __restrict__ out, int64_t rows, int mode) {
+  const int64_t n = rows * 63;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / 63;
+    const int c = (int)(i - r * 63);
+    float v;
+    if (mode == 0) {
+      const int j = c / 3, d = c - j * 3;
+      v = d == 2 ? 1.0f : pred[r * 42 + 2 * j + d];
+    } else {
+      const int d = c / 21, j = c - d * 21;
+      v = d == 2 ? 0.0f : pred[r * 42 + 2 * j + d];
+    }
+    out[i] = v;
+  }
+}
+
+int launch_format_prediction(const float* pred, float* out, int64_t rows, int mode, cudaStream_t stream) {
+  if (rows == 0) return B2H_OK;
+  int64_t blocks = (rows * 63 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  format_prediction_kernel<<<(unsigned)blocks, 256, 0, stream>>>(pred, out, rows, mode);
+  count_launch();
+  return check_launch("format_prediction_kernel");
+}
+
 int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t stream) {
   pack_kernel<<<(g.P + 255) / 256, 256, 0, stream>>>(params, reinterpret_cast<char*>(packed), g);
   count_launch();

@@ -234,3 +234,18 @@ class ConvModel(nn.Module):
         if not self._is_flat():
             self._flatten()
         return self._forward_impl(inp, lengths=lengths, out_scale=1.0 if denormalize is None else float(denormalize))
+
+
+def format_prediction(prediction, fmt="openpose"):
+    """(..., 21, 2) predictions -> (..., 63) rows in the reference's writer layouts:
+    "openpose" = [x,y,1.0]*21 (array2open_pose, steps/utils.py:355-364), "h5" = [x*21 | y*21 | 0*21]
+    (order_and_reshape_toh5, steps/traintest.py:302-317).  Pure data movement on the GPU (bit-exact)."""
+    _lib.require_device(prediction, "prediction")
+    if prediction.shape[-2:] != (21, 2) or prediction.dtype != torch.float32:
+        raise RuntimeError("format_prediction expects float32 (..., 21, 2)")
+    mode = {"openpose": 0, "h5": 1}[fmt]
+    p = prediction.contiguous()
+    rows = p.numel() // 42
+    out = torch.empty(p.shape[:-2] + (63,), dtype=torch.float32, device=p.device)
+    _lib.check(_lib.load().b2h_format_prediction(_lib.ptr(p), _lib.ptr(out), rows, mode, _lib.stream_ptr(p.device)))
+    return out

@@ -135,6 +135,11 @@ int b2h_pose_l1(const float* pred, const float* target, const float* scores, con
                 int T, int row_elems, int loss_kind, float* loss_out, float* d_pred, float* row_scratch,
                 void* stream);
 
+/* Inference output formats (after the fused de-normalise of b2h_conv_forward): pred (rows,42) -> out (rows,63).
+ * mode 0 = OpenPose hand rows [x,y,1.0]*21 (array2open_pose, steps/utils.py:355-364);
+ * mode 1 = packed H5 rows [x*21 | y*21 | 0*21] (order_and_reshape_toh5, steps/traintest.py:302-317). */
+int b2h_format_prediction(const float* pred, float* out, int64_t rows, int mode, void* stream);
+
 /* ---- K3 fused Adam ------------------------------------------------------------------------------
  * torch.optim.Adam.step with torch defaults (steps/traintest.py:48,121) over the flat buffer:
  * g = grads*grad_scale (grad_scale = 1/world for data parallel); m,v,p updated in place; when

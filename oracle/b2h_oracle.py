@@ -411,6 +411,18 @@ def adam_conditioned(grads_per_step, weights, lr, eps=1e-8, margin=3.0):
     return masks
 
 
+def array2open_pose(array):
+    """steps/utils.py:355-364: (21,2) -> flat [x,y,1.0]*21 (confidence defaults to ones)."""
+    a = np.concatenate((np.asarray(array), np.zeros((21, 1)) + 1.0), axis=1)
+    return np.reshape(a, (-1)).astype(np.float32)
+
+
+def order_and_reshape_toh5(frame_prediction):
+    """steps/traintest.py:302-317: (n,21,2) -> (n,63) rows [x*21 | y*21 | 0*21]."""
+    fp = np.pad(np.asarray(frame_prediction), ((0, 0), (0, 0), (0, 1)))
+    return fp.transpose(0, 2, 1).reshape(fp.shape[0], -1)
+
+
 def l1_to_pixels(loss, num_joints=21, upsample=1280):
     """L12Pixels  steps/utils.py:291-299"""
     return loss / num_joints * upsample

@@ -125,3 +125,17 @@ def test_streaming_pipeline_k0_to_k1(stride):
         y = m.predict(x, denormalize=1280)                                                 # traintest.py:270-271
         _tc_clean()
         assert oracle.rel_err(y.cpu().numpy(), ref) <= TOL[prec]
+
+
+def test_inference_output_formats():
+    """de-normalised prediction -> OpenPose rows / packed H5 rows, bit-exact vs the reference writers' layout."""
+    g = load_golden("convmodel_c30.npz")
+    m = _model(golden_sd(g), 30, False, "fp32")
+    y = m.predict(torch.from_numpy(g["input_kp"]).to(DEV), denormalize=1280)
+    op = b2h.format_prediction(y, "openpose").cpu().numpy()
+    h5 = b2h.format_prediction(y, "h5").cpu().numpy()
+    yc = y.cpu().numpy()
+    for b in range(yc.shape[0]):
+        assert np.array_equal(h5[b], oracle.order_and_reshape_toh5(yc[b]))
+        for t_ in (0, 17, yc.shape[1] - 1):
+            assert np.array_equal(op[b, t_], oracle.array2open_pose(yc[b, t_]))
