@@ -135,6 +135,17 @@ __device__ __forceinline__ void scatter_packed(const Geo& g, char* packed, int i
 }
 
 
+// beta^t for an integer step count by binary exponentiation (~2*log2(t) DMULs instead of a double-precision pow())
+__host__ __device__ inline double ipow(double b, long long t) {
+  double r = 1.0;
+  while (t > 0) {
+    if (t & 1) r *= b;
+    b *= b;
+    t >>= 1;
+  }
+  return r;
+}
+
 // Optional tail of the tensor-core train kernel: cross-CTA gradient reduction, (data-parallel) gradient exchange
 // over peer memory and Adam, all inside the SAME cooperative launch (grid barriers through `sync`).
 struct FuseAdam {

@@ -86,9 +86,9 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
   __shared__ float s_step_size, s_inv_bc2_sqrt;
   if (a.step_dev) {   // bias corrections from the device-side step counter (graph replay)
     if (threadIdx.x == 0) {
-      const double t = (double)*a.step_dev;
-      s_step_size = (float)(a.lr_d / (1.0 - pow(a.beta1_d, t)));
-      s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(a.beta2_d, t)));
+      const long long t = *a.step_dev;
+      s_step_size = (float)(a.lr_d / (1.0 - ipow(a.beta1_d, t)));
+      s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - ipow(a.beta2_d, t)));
     }
     __syncthreads();
     a.step_size = s_step_size;
@@ -144,9 +144,9 @@ __global__ void __launch_bounds__(256) adam_dp_kernel(AdamDpArgs d) {
   const size_t P = (size_t)a.n;
   const size_t flag_off = 2 * P;                       // in floats; flags are 8-byte aligned (2P is even)
   if (threadIdx.x == 0) {
-    const double t = (double)*a.step_dev;
-    s_step_size = (float)(a.lr_d / (1.0 - pow(a.beta1_d, t)));
-    s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(a.beta2_d, t)));
+    const long long t = *a.step_dev;
+    s_step_size = (float)(a.lr_d / (1.0 - ipow(a.beta1_d, t)));
+    s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - ipow(a.beta2_d, t)));
   }
   if (blockIdx.x == 0 && threadIdx.x < d.world) {
     __threadfence_system();

@@ -607,10 +607,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       __shared__ float s_step_size, s_inv_bc2_sqrt;
       grid_barrier(f.sync, tid);                         // every CTA's partial slice is visible
       B2H_STAMP();   // tail: grid barrier passed
-      if (tid == 0) {
-        const double tt = (double)*f.step_dev;
-        s_step_size = (float)(f.lr / (1.0 - pow(f.beta1, tt)));
-        s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow(f.beta2, tt)));
+      if (tid == kTileThreads - 1) {                     // last thread: usually idle in the gather below
+        const long long tt = *f.step_dev;
+        s_step_size = (float)(f.lr / (1.0 - ipow(f.beta1, tt)));
+        s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - ipow(f.beta2, tt)));
       }
       if (blockIdx.x == 0 && warp == 7 && f.loss_out) {  // loss = sum of the CTAs' loss partials (fixed order)
         float sl = 0.f;
@@ -619,7 +619,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
         if (lane == 0) *f.loss_out = sl;
       }
-      __syncthreads();
       const int nj = gp_total(g);                        // multiple of 4: every slice is float4-addressable
       const int nparts = (int)gridDim.x;
       const int per = round_up((nj + nparts - 1) / nparts, 4);
@@ -661,6 +660,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           }
         }
         __syncthreads();
+        B2H_STAMP();   // tail: gather done
         const float* red = reinterpret_cast<const float*>(red4);
         for (int j = jb + tid; j < jn; j += kTileThreads) {
           float gr = 0.f;
