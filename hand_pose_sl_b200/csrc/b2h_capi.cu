@@ -115,7 +115,7 @@ extern "C" int b2h_conv_forward(const void* x, int x_dtype, const float* params,
     a.y = y; a.B = B; a.T = T; a.apply_mask = apply_mask; a.mode = 0; a.out_scale = out_scale; a.geo = g;
     return launch_fp32(a, false, (cudaStream_t)stream, 0);
   } else if (precision == B2H_BF16) {
-    if (tc_tile_ok(g, T, false))   // independent 128-row tiles (T <= 126): persistent tile kernel
+    if (tc_tile_ok(g, T, false))   // independent 128/256-row tiles (T <= 256): persistent tile kernel
       return launch_tc_tile_fwd(x, x_dtype, params, reinterpret_cast<const char*>(packed), lengths, y, B, T, apply_mask, out_scale, g,
                                 (cudaStream_t)stream);
     TcFwdArgs a{};                 // long windows: layer-major row-space kernel
@@ -154,7 +154,7 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
   if (workspace_bytes < need) { set_error("%s: workspace %lld B < %lld B", who, (long long)workspace_bytes, (long long)need); return B2H_EWORKSPACE; }
   partials = reinterpret_cast<float*>(workspace);
   loss_partials = partials + (size_t)nparts * stride;
-  // fp32 mode: FFMA kernel.  bf16 mode: tcgen05 tile kernel (T <= 126, C <= 32); other bf16 shapes fall
+  // fp32 mode: FFMA kernel.  bf16 mode: tcgen05 tile kernel (T <= 256, C <= 32); other bf16 shapes fall
   // back to the FFMA kernel -- still CUDA, still fp32 master weights.
   Fp32Args a{};
   a.x = x; a.x_dtype = x_dtype; a.target = target; a.conf = conf; a.d_y = d_y; a.lengths = lengths; a.params = params;

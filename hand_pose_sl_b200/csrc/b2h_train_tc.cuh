@@ -11,7 +11,8 @@
 //   mode B (T <= 64): two segments of 64 rows, one M=64 MMA each (TMEM lanes 32q+i and 32q+16+i), every
 //                     segment holding g = floor(66/(T+2)) whole windows -> T=64: 2 windows per tile, no
 //                     padded-row waste; the two segments are issued by two different warps;
-//   mode A (64 < T <= 126): one segment of 128 rows, M=128, one window.
+//   mode A (64 < T <= 256): one segment of 128*NT rows (NT = 1 for T <= 128, else 2), one window, NT M=128 MMAs per
+//                     conv tap issued by NT warps into NT accumulators (TMEM columns 64j); every thread then owns NT rows.
 // A segment lives in shared memory as [2 zero rows][window][2 zero rows][window]...[zero rows] in the
 // no-swizzle K-major canonical layout [channel/8][row][8 ch] (16-B rows), so conv tap k is a +k change of
 // the A descriptor's start-address field and the SAME buffer also serves, read as an MN-major operand, as
@@ -46,13 +47,13 @@ struct TcTileArgs {
   FuseAdam fuse;
   int B, T, loss_kind, apply_mask, mode;   // mode 0 = forward only, 1 = train (loss inside), 2 = backward of given d_y
   float out_scale;
-  int n_tiles, nhalf, MB, HR, gh;          // tile geometry
+  int n_tiles, nhalf, MB, HR, gh, NT;      // tile geometry (NT = 128-row MMA tiles per segment: 2 for 128 < T <= 256)
   Geo geo;
 };
 
 constexpr int kTileThreads = 256;   // 8 warps: two per TMEM lane quadrant (each takes every other 16-column chunk)
 constexpr int kAccCol = 0;        // forward / dgrad accumulator: columns [0, 64)
-constexpr int kWgCol = 64;        // weight-gradient accumulators: 2 layer pairs x (5 taps x 32 + 8 bias) columns
+// weight-gradient accumulators follow the forward/dgrad accumulators: 2 layer pairs x (5 taps x 32 + 8 bias) columns
 constexpr int kWgPairCols = 5 * 32 + 8;
 constexpr int kDpMaxCta = 160;    // flag slots per rank in the data-parallel exchange buffer (>= CTAs of the train kernel)
 
@@ -165,7 +166,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   __shared__ __align__(16) float bias_s[4][64];
   __shared__ float red_s[8];
   const Geo& g = p.geo;
-  const int T = p.T, MB = p.MB, HR = p.HR, nhalf = p.nhalf, gh = p.gh;
+  const int T = p.T, MB = p.MB, HR = p.HR, nhalf = p.nhalf, gh = p.gh, NT = p.NT;
+  const int kWgCol = 64 * NT;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform
   const int rows = nhalf * HR;
@@ -186,16 +188,30 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   const int ch = warp >> 2;                      // column half: chunks c0 = 16*ch, 16*ch + 32, ...
   const int hh = (nhalf == 2) ? ((r128 >> 4) & 1) : 0;
   const int m = (nhalf == 2) ? ((r128 >> 5) * 16 + (r128 & 15)) : r128;
-  const int row = hh * HR + 2 + m;
-  const int wj = m / (T + 2), t = m - wj * (T + 2);
+  // row context of this thread in MMA tile j of its segment (NT > 1 only with one 128*NT-row segment per tile)
+  struct RowCtx { int row, t, gw; bool valid; };
+  auto rowctx = [&](int j, int wbase) {
+    const int mm = m + 128 * j;
+    const int wjj = mm / (T + 2);
+    RowCtx r;
+    r.t = mm - wjj * (T + 2);
+    r.row = hh * HR + 2 + mm;
+    r.gw = wbase + hh * gh + wjj;
+    r.valid = (r.t < T) && (wjj < gh) && (r.gw < p.B);
+    return r;
+  };
+  const int wj = m / (T + 2), t = m - wj * (T + 2);     // tile 0 (prefetch path, NT == 1)
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
   const int srow = hh * MB + m;                  // row of this thread in the fp32 staging tile
-  const bool bulk_io = (T & 1) == 0;             // T*168 B and the staging row offsets are 16-B multiples
+  const bool bulk_io = (T & 1) == 0 && NT == 1;  // T*168 B and the staging row offsets are 16-B multiples
   const int wpt = nhalf * gh;                    // windows per tile
-  const int nissue = nhalf;                      // issuing warps: one per row segment
+  const int nissue = (nhalf == 2) ? 2 : NT;      // issuing warps: one per row segment / per 128-row MMA tile
   const uint32_t idesc_M = (nhalf == 2) ? 64 : 128;
   const int n_in = g.n_in;
-  const bool fast_in = (g.pos_emb == 0) && ((n_in & 7) == 0) && n_in <= 24 * 1 + 8;   // <= 4 chunks, register prefetch
+  const bool vec_in = (g.pos_emb == 0) && ((n_in & 7) == 0) && n_in <= 32;   // <= 4 chunks: 16-B vector loads
+  const bool fast_in = vec_in && NT == 1;        // + register prefetch one tile ahead
+  const int seg_row = (nhalf == 2) ? HR : 128;   // row offset / TMEM offset of issuing warp w's accumulator
+  const uint32_t seg_d = (nhalf == 2) ? (16u << 16) : 64u;
   const int cpr = n_in >> 3;
 
   // ---- input prefetch registers (one tile ahead) ----
@@ -219,7 +235,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   };
   prefetch_x(blockIdx.x);
 
-  if (warp == 0) tmem_alloc(&tmem_slot, TRAIN ? 512 : 64);
+  if (warp == 0) tmem_alloc(&tmem_slot, TRAIN ? 512 : 64 * NT);
   if (tid == 0) {
     mbar_init(&bar, nissue);
     mbar_init(&wbar, 1);
@@ -300,10 +316,6 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
 
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const int wbase = tile * wpt;
-    const int gw = wbase + hh * gh + wj;           // this thread's global window
-    const bool valid = (t < T) && (wj < gh) && (gw < p.B);
-    int len = T;
-    if (valid && p.lengths) { len = p.lengths[gw]; len = len < 0 ? 0 : (len > T ? T : len); }
 
     const bool tgt_smem = TRAIN && p.mode == 1 && bulk_io;
     if (tid == 0) {
@@ -319,11 +331,26 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         }
       }
     }
-    // ---- stage inputs: one thread per row, (n_in) channels NWC -> X [chunk][row][8] bf16 ----
-    {
+    // ---- stage inputs: one thread per row (and per MMA tile j), (n_in) channels NWC -> X [chunk][row][8] bf16 ----
+    for (int j = 0; j < NT; ++j) {
+      const RowCtx rc = rowctx(j, wbase);
+      const int row = rc.row;
       const int pe = g.pos_emb;
       const int nch0 = g.kp[0] / 8;
-      if (valid && fast_in) {
+      if (rc.valid && vec_in) {
+        if (!fast_in) {   // no prefetch (NT > 1): load this row now
+          if (p.x_dtype == B2H_DT_F32) {
+            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + ((size_t)rc.gw * T + rc.t) * n_in);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c < 2 * cpr && ((c >> 1) & 1) == ch) xf[c] = __ldg(src + c);
+          } else {
+            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + ((size_t)rc.gw * T + rc.t) * n_in);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < cpr && (c & 1) == ch) xb[c] = __ldg(src + c);
+          }
+        }
         if (p.x_dtype == B2H_DT_F32) {
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8)
@@ -337,16 +364,16 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           for (int c8 = 0; c8 < 4; ++c8)
             if (c8 < cpr && (c8 & 1) == ch) *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = xb[c8];
         }
-      } else if (valid) {
+      } else if (rc.valid) {
         for (int c8 = ch; c8 < nch0; c8 += 2) {
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int cc = c8 * 8 + e;            // channel in the conv1 input (pos-emb row first)
             float val = 0.0f;
-            if (pe && cc == 0) val = __fdiv_rn((float)t, 100.0f);                // HandPoseModels.py:70-82
+            if (pe && cc == 0) val = __fdiv_rn((float)rc.t, 100.0f);             // HandPoseModels.py:70-82
             else if (cc - pe < n_in && cc - pe >= 0) {
-              const size_t gi = ((size_t)gw * T + t) * n_in + (cc - pe);
+              const size_t gi = ((size_t)rc.gw * T + rc.t) * n_in + (cc - pe);
               val = (p.x_dtype == B2H_DT_F32) ? __ldg(reinterpret_cast<const float*>(p.x) + gi)
                                               : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.x)[gi]);
             }
@@ -360,7 +387,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       }
       if (TRAIN && ch == 0) {   // ones column (B operand of the bias-gradient GEMM): 1 on real frames
         uint4 o = make_uint4(0, 0, 0, 0);
-        if (valid) o.x = 0x00003F80u;             // bf16(1.0) in element 0
+        if (rc.valid) o.x = 0x00003F80u;          // bf16(1.0) in element 0
         *reinterpret_cast<uint4*>(ONES + (size_t)row * 16) = o;
       }
     }
@@ -382,9 +409,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         if (elect_one()) {
           const uint32_t idesc = make_idesc_bf16(idesc_M, N, 0, 0);
           // output row 2+m of segment h reads input row m+k  ->  start row = h*HR + k
-          const uint32_t a_lo = desc_lo(smem_u32(bin), (uint32_t)CH) + warp * HR;
+          const uint32_t a_lo = desc_lo(smem_u32(bin), (uint32_t)CH) + warp * seg_row;
           const uint32_t b_lo = desc_lo(smem_u32(smem + L.wf[l]), (uint32_t)N * 16);
-          issue_conv(acc_d + ((uint32_t)(warp * 16) << 16), a_lo, hi_k, b_lo, hi_k, KS, N, rows, idesc);
+          issue_conv(acc_d + warp * seg_d, a_lo, hi_k, b_lo, hi_k, KS, N, rows, idesc);
           umma_commit(&bar);
         }
         __syncwarp();
@@ -394,7 +421,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       phase ^= 1;
       tc_fence_after();
       B2H_STAMP();   // fwd layer: accumulator ready
-      const uint32_t taddr = tbase + lane_addr + kAccCol;
+      float contrib = 0.f;
+      for (int j = 0; j < NT; ++j) {
+      const RowCtx rc = rowctx(j, wbase);
+      const int row = rc.row, t = rc.t, gw = rc.gw;
+      const bool valid = rc.valid;
+      const uint32_t taddr = tbase + lane_addr + kAccCol + 64 * j;
       if (l < 3) {
         for (int c0 = 16 * ch; c0 < N; c0 += 32) {
           uint32_t v[16];
@@ -408,6 +440,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         }
       } else {
         // layer 4 epilogue: prediction (+ mask_output), and in train mode the criterion and d(loss)/d(pred)
+        int len = T;
+        if (valid && p.lengths) { len = p.lengths[gw]; len = len < 0 ? 0 : (len > T ? T : len); }
         float n_el = 0.f, scale = 0.f;
         const float* tg = nullptr; const float* cf = nullptr; const float* dy = nullptr;
         if (TRAIN && valid) {
@@ -423,7 +457,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         const bool y_smem = !TRAIN && bulk_io;
         float* yrow = (valid && p.y) ? p.y + ((size_t)gw * T + t) * B2H_COUT : nullptr;          // global row
         float* ys_row = YS + (size_t)srow * B2H_COUT;                                            // shared staging row
-        if (tgt_smem) { mbar_wait(&tbar, tphase, 18); tphase ^= 1; }
+        if (tgt_smem && j == 0) { mbar_wait(&tbar, tphase, 18); tphase ^= 1; }
         B2H_STAMP();   // layer-4 epilogue: target tile landed
         float sum = 0.f;
         for (int c0 = 16 * ch; c0 < N; c0 += 32) {
@@ -484,13 +518,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           }
           B2H_STAMP();   // layer-4 epilogue: one 16-column chunk done
         }
-        if (TRAIN && p.mode == 1) {
-          // per-sample mean = sum_{t<len} |d| / (len*42)  (utils.py:426 / :450): accumulate sum/n_el
-          float contrib = (valid && t < len) ? sum / n_el : 0.f;
+        // per-sample mean = sum_{t<len} |d| / (len*42)  (utils.py:426 / :450): accumulate sum/n_el
+        if (TRAIN && p.mode == 1) contrib += (valid && t < len) ? sum / n_el : 0.f;
+      }
+      }   // MMA tiles j
+      if (TRAIN && p.mode == 1 && l == 3) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
-          if (lane == 0) red_s[warp] = contrib;
-        }
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        if (lane == 0) red_s[warp] = contrib;
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -520,9 +555,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
             if (l > 0) {  // dgrad: dA_{l-1}[r][ci] = sum_{k',co} dZ_l[r+k'-2][co] * W_l[co][ci][4-k']
               const int KSd = round_up(g.cout[l], 16) >> 4, Nd = round_up(g.cin[l], 16);
               const uint32_t idesc = make_idesc_bf16(idesc_M, Nd, 0, 0);
-              const uint32_t a_lo = desc_lo(smem_u32(gz), (uint32_t)CH) + warp * HR;
+              const uint32_t a_lo = desc_lo(smem_u32(gz), (uint32_t)CH) + warp * seg_row;
               const uint32_t b_lo = desc_lo(smem_u32(smem + L.wd[l]), (uint32_t)Nd * 16);
-              issue_conv(acc_d + ((uint32_t)(warp * 16) << 16), a_lo, hi_k, b_lo, hi_k, KSd, Nd, rows, idesc);
+              issue_conv(acc_d + warp * seg_d, a_lo, hi_k, b_lo, hi_k, KSd, Nd, rows, idesc);
               umma_commit(&bar);
             }
             // wgrad: dW_l[k][co][ci] += sum_r dZ_l[r][co] * in_l[r+k-2][ci];  db_l[co] += sum_r dZ_l[r][co]
@@ -558,7 +593,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         if (l > 0) {
           // dZ_{l-1} = dA_{l-1} * (a_{l-1} > 0)     (ReLU backward on the saved activation)
           const int Nd = round_up(g.cin[l], 16);
-          const uint32_t taddr = tbase + lane_addr + kAccCol;
+          for (int j = 0; j < NT; ++j) {
+          const RowCtx rc = rowctx(j, wbase);
+          const int row = rc.row;
+          const bool valid = rc.valid;
+          const uint32_t taddr = tbase + lane_addr + kAccCol + 64 * j;
           for (int c0 = 16 * ch; c0 < Nd; c0 += 32) {
             uint32_t v[16];
             tmem_ld16(taddr + c0, v);
@@ -571,6 +610,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
             store8_bf16(gnext, CH, row, c0 >> 3, f);
             store8_bf16(gnext, CH, row, (c0 >> 3) + 1, f + 8);
           }
+          }   // MMA tiles j
         }
         if (l == 1 && tile + (int)gridDim.x >= p.n_tiles) {
           // last tile of this CTA: W_4 and W_3 (layer pair 1) are final (their MMAs precede the commit just waited
@@ -699,19 +739,24 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   B2H_STAMP();   // readout done
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tbase, TRAIN ? 512 : 64);
+  if (warp == 0) tmem_dealloc(tbase, TRAIN ? 512 : 64 * NT);
 }
 
 // ---- host side ----
+inline size_t tc_tile_smem(const Geo& g, int T, bool train) {
+  const int MB = T <= 64 ? 64 : (T > 128 ? 256 : 128), nhalf = T <= 64 ? 2 : 1;
+  return (size_t)tile_smem_layout(g, nhalf * (MB + 8), train).total;
+}
+
 inline bool tc_tile_supported(const Geo& g, int T, bool train) {
-  if (T < 1 || T > 126) return false;
-  if (g.kp[0] > 32 || g.kp[1] > 32) return !train && g.kp[0] <= 64 && g.kp[1] <= 64;
-  return true;
+  if (T < 1 || T > 256) return false;
+  if ((g.kp[0] > 32 || g.kp[1] > 32) && (train || g.kp[0] > 64 || g.kp[1] > 64)) return false;
+  return tc_tile_smem(g, T, train) <= (size_t)225 * 1024;
 }
 
 inline void tc_tile_plan(const Geo& g, int B, int T, bool train, TcTileArgs& p, size_t& smem, int& grid) {
-  if (T <= 64) { p.nhalf = 2; p.MB = 64; }
-  else { p.nhalf = 1; p.MB = 128; }
+  if (T <= 64) { p.nhalf = 2; p.MB = 64; p.NT = 1; }
+  else { p.nhalf = 1; p.NT = (T > 128) ? 2 : 1; p.MB = 128 * p.NT; }
   p.HR = p.MB + 8;
   p.gh = (p.MB + 2) / (T + 2);
   const int wpt = p.nhalf * p.gh;

@@ -50,7 +50,8 @@ def test_forward_golden(name, prec):
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 @pytest.mark.parametrize("B,T,C", [(1, 64, 30), (7, 64, 30), (5, 1, 30), (3, 5, 30), (2, 130, 30), (9, 33, 16), (2, 64, 64),
-                                   (300, 64, 30)])
+                                   (300, 64, 30), (3, 127, 30), (2, 128, 30), (3, 129, 30), (5, 200, 30), (2, 256, 30),
+                                   (2, 257, 30), (2, 200, 64), (150, 200, 30)])
 def test_forward_vs_oracle_shapes(B, T, C, prec):
     sd = oracle.init_params(C, False, seed=B + T)
     batch = synthetic.model_batch(B, T, seed=B * 1000 + T)
