@@ -118,6 +118,9 @@ extern "C" int b2h_conv_forward(const void* x, int x_dtype, const float* params,
     if (tc_tile_ok(g, T, false))   // independent 128/256-row tiles (T <= 256): persistent tile kernel
       return launch_tc_tile_fwd(x, x_dtype, params, reinterpret_cast<const char*>(packed), lengths, y, B, T, apply_mask, out_scale, g,
                                 (cudaStream_t)stream);
+    if (!tc_fwd_supported(g, T) && tc_wide_supported(g, T))   // wide models (C <= 256): weights streamed through smem
+      return launch_tc_wide_fwd(x, x_dtype, params, reinterpret_cast<const char*>(packed), lengths, y, B, T, apply_mask, out_scale, g,
+                                (cudaStream_t)stream);
     TcFwdArgs a{};                 // long windows: layer-major row-space kernel
     a.x = x; a.x_dtype = x_dtype; a.params = params; a.packed = reinterpret_cast<const char*>(packed); a.lengths = lengths;
     a.y = y; a.B = B; a.T = T; a.apply_mask = apply_mask; a.out_scale = out_scale; a.geo = g;

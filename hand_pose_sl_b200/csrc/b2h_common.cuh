@@ -196,6 +196,9 @@ struct TcFwdArgs {
   Geo geo;
 };
 int launch_tc_fwd(TcFwdArgs& p, cudaStream_t stream);
+bool tc_wide_supported(const Geo& g, int T);
+int launch_tc_wide_fwd(const void* x, int x_dtype, const float* params, const char* packed, const int32_t* lengths, float* y,
+                       int B, int T, int apply_mask, float out_scale, const Geo& g, cudaStream_t stream);
 bool tc_fwd_supported(const Geo& g, int T);
 int launch_tc_probe(const void* a, const void* b, float* out, int n, int ksteps, int shift, int variant, cudaStream_t stream);
 int tc_status_and_clear();

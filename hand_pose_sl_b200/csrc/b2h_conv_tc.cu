@@ -412,3 +412,4 @@ int launch_tc_bench(long long* out, int M, int N, int reps, int nacc, int mn_maj
 }  // namespace b2h
 
 #include "b2h_train_tc.cuh"
+#include "b2h_wide_tc.cuh"

@@ -63,6 +63,27 @@ def test_forward_vs_oracle_shapes(B, T, C, prec):
     assert oracle.rel_err(y.cpu().numpy(), ref) <= TOL[prec]
 
 
+@pytest.mark.parametrize("B,T,C", [(4, 64, 256), (7, 64, 128), (5, 64, 80), (3, 126, 256), (2, 200, 256), (3, 256, 96),
+                                   (450, 64, 256)])
+def test_wide_forward_vs_oracle(B, T, C):
+    """conv_channels > 64 in bf16 mode: the streamed-weight kernel (256-row tiles, weight ring; 450 windows of 64 frames
+    = 150 tiles > 148 CTAs, so the ring and the phases wrap across tiles).  Also with mask_output + de-normalisation."""
+    sd = oracle.init_params(C, False, seed=B + T)
+    batch = synthetic.model_batch(B, T, seed=B * 1000 + T, ragged=True, len_seed=C)
+    m = _model(sd, C, False, "bf16")
+    with torch.no_grad():
+        y = m(batch["input_kp"].to(DEV))
+        ym = m.predict(batch["input_kp"].to(DEV), lengths=batch["n_frames"], denormalize=1280.0)
+    _tc_clean()
+    ref = oracle.conv_model_forward(sd, batch["input_kp"]).contiguous()
+    assert oracle.rel_err(y.cpu().numpy(), ref.numpy()) <= TOL["bf16"]
+    refm = oracle.mask_output(ref.clone(), batch["n_frames"]) * 1280.0
+    assert oracle.rel_err(ym.cpu().numpy(), refm.numpy()) <= TOL["bf16"]
+    lens = batch["n_frames"]
+    for i in range(min(B, 8)):
+        assert float(ym[i, int(lens[i]):].abs().max() if int(lens[i]) < T else 0.0) == 0.0
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_bf16_input_tensor(prec):
     sd = oracle.init_params(30, False, seed=0)
