@@ -13,12 +13,15 @@
 //     the descriptor start address) that every layer reads and then overwrites IN PLACE: all MMAs of a layer have
 //     completed (commit -> acc_full) before its epilogue writes, and inference keeps no activations;
 //   * the packed UMMA B blocks (b2h_common.cuh umma_b_offset: one [2][N][8] block per (tap, 16-channel k-step),
-//     contiguous in global memory) stream through a ring of 8-KB stages by 1-D TMA bulk copies issued by a dedicated
-//     producer warp that runs ahead across layers and tiles; full[]/empty[] mbarriers, the empty side armed by
-//     tcgen05.commit of the MMAs that read the stage;
+//     contiguous in global memory) stream through a ring of 16-KB stages by TMA tensor-map loads (the packed sections
+//     viewed as a 2-D tensor of 128-byte rows, box = 128 rows; measured here: 1-D cp.async.bulk copies top out at
+//     ~23 B/cycle/SM, a third of what two N=256 MMAs per stage consume) issued by a dedicated producer warp that
+//     runs ahead across layers and tiles; full[]/empty[] mbarriers, the empty side armed by tcgen05.commit of the
+//     MMAs that read the stage;
 //   * warp roles: 8 epilogue warps (two per TMEM lane quadrant, alternating 32-column chunks: tcgen05.ld -> bias/ReLU
 //     -> bf16 -> st.shared, or the fp32 prediction rows of layer 4), 1 MMA-issuing warp, 1 weight-producer warp.
 #pragma once
+#include <cuda.h>   // CUtensorMap + enums only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
 
 namespace b2h {
 using namespace tc;
@@ -37,7 +40,8 @@ struct WideArgs {
 constexpr int kWideThreads = 320;
 constexpr int kWideEpiThreads = 256;
 constexpr int kWideRows = 264;            // 2 zero rows + 256 output rows + 6 zero rows
-constexpr int kWideStage = 8192;          // bytes per ring stage (one N=256 block, or several narrower ones)
+constexpr int kWideStage = 16384;         // bytes per ring stage (two N=256 blocks, or several narrower ones)
+constexpr int kWideBoxRows = kWideStage / 128;
 constexpr int kWideMaxStages = 16;
 
 struct WideSched { int KS, N, blk_bytes, nblk, bps, nst; };
@@ -51,7 +55,33 @@ __host__ __device__ inline WideSched wide_sched(const Geo& g, int l) {
   return s;
 }
 
-__global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_fwd_kernel(WideArgs p) {
+// raw shared-address variants of the barrier / TMA / commit helpers for the two single-thread loops
+__device__ __forceinline__ void tma_load_2d_addr(uint32_t smem_dst, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void expect_tx_addr(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void commit_addr(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool wait_addr(uint32_t bar, uint32_t parity, int site) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  if (ok) return true;                               // fast path: no clock reads
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return true;
+    if (clock64() - t0 > 4000000000LL) { atomicExch(&g_tc_status, site); return false; }
+  }
+}
+
+__global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_fwd_kernel(WideArgs p, const __grid_constant__ CUtensorMap wmap) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[kWideMaxStages];    // stage landed (TMA complete_tx)
   __shared__ __align__(8) uint64_t empty_bar[kWideMaxStages];   // stage consumed (tcgen05.commit)
@@ -92,21 +122,28 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_fwd_kernel(WideA
   tc_fence_after();
   const uint32_t tbase = tmem_slot;
 
+  // Both single-thread loops below are latency-bound scalar code (every instruction waits for the previous one): a
+  // first version that recomputed slot = stage % S, the barrier addresses and the descriptors per stage needed ~540
+  // cycles per stage -- twice the 258 tensor cycles of the two N=256 MMAs it feeds.  So: raw shared-memory addresses
+  // computed once, ring position and parity carried as counters, descriptors advanced by one add.
+  const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]), ring0 = smem_u32(RING);
   if (warp == 9) {
     // ===================== weight producer: one thread, runs ahead by the ring depth =====================
     if (elect_one()) {
-      uint32_t gs = 0;
+      uint32_t slot = 0, ph = 1;                     // parity 1 on a fresh barrier = "already free" (first lap)
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
         for (int l = 0; l < 4; ++l) {
           const WideSched sc = wide_sched(g, l);
-          const char* src = p.packed + g.tf_off[l];
-          for (int st = 0; st < sc.nst; ++st, ++gs) {
-            const uint32_t slot = gs % S, use = gs / S;
-            if (use > 0 && !mbar_wait(&empty_bar[slot], (use - 1) & 1, 60)) return;
-            int nb = sc.nblk - st * sc.bps; nb = nb > sc.bps ? sc.bps : nb;
-            const uint32_t bytes = (uint32_t)nb * sc.blk_bytes;
-            mbar_arrive_expect_tx(&full_bar[slot], bytes);
-            bulk_g2s(RING + (size_t)slot * kWideStage, src + (size_t)st * sc.bps * sc.blk_bytes, bytes, &full_bar[slot]);
+          int row = (int)((g.tf_off[l] - g.tf_off[0]) >> 7);            // 128-byte rows of the weight tensor map
+          const int rows_per_stage = (sc.bps * sc.blk_bytes) >> 7;
+          for (int st = 0; st < sc.nst; ++st) {
+            if (!wait_addr(empty0 + slot * 8, ph, 60)) return;
+            // one 128-row box = 16 KB whatever the stage's payload is (rows past it belong to the next stage / are
+            // zero-filled past the tensor): the transaction count is always the full box
+            expect_tx_addr(full0 + slot * 8, kWideStage);
+            tma_load_2d_addr(ring0 + slot * kWideStage, &wmap, 0, row, full0 + slot * 8);
+            row += rows_per_stage;
+            if (++slot == (uint32_t)S) { slot = 0; ph ^= 1; }
           }
         }
     }
@@ -114,35 +151,44 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_fwd_kernel(WideA
   } else if (warp == 8) {
     // ===================== MMA issuer: one thread =====================
     if (elect_one()) {
-      uint32_t gs = 0, act_phase = 0;
+      uint32_t slot = 0, ph = 0, act_phase = 0;
+      int dn = 0;
       const uint32_t hi_k = desc_hi(128);
       const uint32_t a_lo0 = desc_lo(smem_u32(A), (uint32_t)CH);
+      const uint32_t acc_addr = smem_u32(&acc_full);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
         for (int l = 0; l < 4; ++l) {
           const WideSched sc = wide_sched(g, l);
           const uint32_t idesc = make_idesc_bf16(128, sc.N, 0, 0);
+          const uint32_t b_lo0 = desc_lo(ring0, (uint32_t)sc.N * 16);   // + slot * stage + block * blk, in 16-B units
+          const uint32_t blk16 = (uint32_t)sc.blk_bytes >> 4;
           if (!mbar_wait(&act_ready, act_phase, 61)) return;
           act_phase ^= 1;
           tc_fence_after();
-          int k = 0, s = 0;                           // block q = k*KS + s
+          if (p.dbg && blockIdx.x == 0 && dn < 8) p.dbg[dn++] = clock64();   // layer inputs ready
+          int s = 0, left = sc.nblk;
+          uint32_t a_tap = a_lo0, a_cur = a_lo0;       // output row 2+m reads input row m+k: tap k = +k rows
           uint32_t acc = 0;
-          for (int st = 0; st < sc.nst; ++st, ++gs) {
-            const uint32_t slot = gs % S, use = gs / S;
-            if (!mbar_wait(&full_bar[slot], use & 1, 62)) return;
-            tc_fence_after();
-            int nb = sc.nblk - st * sc.bps; nb = nb > sc.bps ? sc.bps : nb;
-            const uint32_t ring = smem_u32(RING + (size_t)slot * kWideStage);
+          for (int st = 0; st < sc.nst; ++st) {
+            // no tcgen05.fence after this wait: the mbarrier orders the TMA writes before the MMAs' reads
+            if (!wait_addr(full0 + slot * 8, ph, 62)) return;
+            uint32_t b_cur = b_lo0 + slot * (kWideStage >> 4);
+            const int nb = left < sc.bps ? left : sc.bps;
+            left -= nb;
             for (int b = 0; b < nb; ++b) {
-              const uint64_t bd = desc64(desc_lo(ring + (uint32_t)b * sc.blk_bytes, (uint32_t)sc.N * 16), hi_k);
-              const uint32_t a_lo = a_lo0 + 2 * s * rows + k;   // output row 2+m reads input row m+k
-              umma_bf16(tbase, desc64(a_lo, hi_k), bd, idesc, acc);
-              umma_bf16(tbase + 256, desc64(a_lo + 128, hi_k), bd, idesc, acc);
+              const uint64_t bd = desc64(b_cur, hi_k);
+              umma_bf16(tbase, desc64(a_cur, hi_k), bd, idesc, acc);
+              umma_bf16(tbase + 256, desc64(a_cur + 128, hi_k), bd, idesc, acc);
               acc = 1;
-              if (++s == sc.KS) { s = 0; ++k; }
+              b_cur += blk16;
+              a_cur += 2 * rows;                       // next 16-channel k-step: two chunks further
+              if (++s == sc.KS) { s = 0; a_tap += 1; a_cur = a_tap; }
             }
-            umma_commit(&empty_bar[slot]);            // stage reusable once these MMAs have read it
+            commit_addr(empty0 + slot * 8);            // stage reusable once these MMAs have read it
+            if (++slot == (uint32_t)S) { slot = 0; ph ^= 1; }
           }
-          umma_commit(&acc_full);
+          commit_addr(acc_addr);
+          if (p.dbg && blockIdx.x == 0 && dn < 8) p.dbg[dn++] = clock64();   // layer MMAs issued
         }
     }
     __syncwarp();
@@ -210,12 +256,14 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_fwd_kernel(WideA
     stage_inputs(blockIdx.x);
     publish();
     uint32_t acc_phase = 0;
+    int en = 64;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       for (int l = 0; l < 4; ++l) {
         const int N = g.np_[l];
         if (!mbar_wait(&acc_full, acc_phase, 63 + l)) return;
         acc_phase ^= 1;
         tc_fence_after();
+        if (p.dbg && blockIdx.x == 0 && tid == 0 && en < 124) p.dbg[en++] = clock64();   // accumulators complete
         for (int j = 0; j < 2; ++j) {
           const RowCtx rc = rowctx(j, tile);
           const uint32_t taddr = tbase + lane_addr + 256 * j;
@@ -260,6 +308,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_fwd_kernel(WideA
         }
         if (l == 3) stage_inputs(tile + gridDim.x);   // the buffer is dead after layer 4's MMAs: next tile's rows go in
         publish();
+        if (p.dbg && blockIdx.x == 0 && tid == 0 && en < 124) p.dbg[en++] = clock64();   // epilogue done
       }
     }
   }
@@ -278,7 +327,7 @@ inline int wide_a_bytes(const Geo& g) {
 
 bool tc_wide_supported(const Geo& g, int T) {
   if (T < 1 || T > 256 || g.C > 256 || g.cin[0] > 64) return false;
-  return (size_t)wide_a_bytes(g) + 4 * kWideStage <= (size_t)220 * 1024;
+  return (size_t)wide_a_bytes(g) + 3 * kWideStage <= (size_t)220 * 1024;
 }
 
 int launch_tc_wide_fwd(const void* x, int x_dtype, const float* params, const char* packed, const int32_t* lengths, float* y,
@@ -286,12 +335,13 @@ int launch_tc_wide_fwd(const void* x, int x_dtype, const float* params, const ch
   WideArgs p{};
   p.x = x; p.x_dtype = x_dtype; p.params = params; p.packed = packed; p.lengths = lengths; p.y = y;
   p.B = B; p.T = T; p.apply_mask = apply_mask; p.out_scale = out_scale; p.geo = g;
+  p.dbg = g_dbg_timing;
   p.gh = 258 / (T + 2);
   p.n_tiles = (B + p.gh - 1) / p.gh;
   p.a_bytes = wide_a_bytes(g);
   int S = (int)(((size_t)220 * 1024 - p.a_bytes) / kWideStage);
   if (S > kWideMaxStages) S = kWideMaxStages;
-  if (S < 4) { set_error("wide tensor-core forward: C=%d leaves no room for the weight ring", g.C); return B2H_ESHAPE; }
+  if (S < 3) { set_error("wide tensor-core forward: C=%d leaves no room for the weight ring", g.C); return B2H_ESHAPE; }
   p.nstage = S;
   const size_t smem = (size_t)p.a_bytes + (size_t)S * kWideStage;
   static size_t attr_bytes = 0;
@@ -302,7 +352,30 @@ int launch_tc_wide_fwd(const void* x, int x_dtype, const float* params, const ch
   }
   int grid = num_sms();
   if (grid > p.n_tiles) grid = p.n_tiles;
-  conv_tc_wide_fwd_kernel<<<grid, kWideThreads, smem, stream>>>(p);
+  // weight tensor map: the forward UMMA sections [tf_off[0], td_off[0]) as rows of 64 bf16 (128 B), box = 64 rows
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || !fn) { cudaGetLastError(); set_error("cuTensorMapEncodeTiled entry point unavailable"); return B2H_ECUDA; }
+    encode = (EncodeTiledFn)fn;
+  }
+  CUtensorMap wmap;
+  {
+    const cuuint64_t gdim[2] = {64, (cuuint64_t)((g.td_off[0] - g.tf_off[0]) >> 7)};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t box[2] = {64, kWideBoxRows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<char*>(packed) + g.tf_off[0], gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return B2H_ECUDA; }
+  }
+  conv_tc_wide_fwd_kernel<<<grid, kWideThreads, smem, stream>>>(p, wmap);
   count_launch();
   return check_launch("conv_tc_wide_fwd_kernel");
 }
