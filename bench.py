@@ -333,6 +333,35 @@ def main():
                                         "frac": f_tfl / pk["tflops"], "hbm_gbs": f_bytes / (f_ms * 1e-3) / 1e9,
                                         "hbm_frac": f_bytes / (f_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
                            "tc_status": int(lib.b2h_tc_status())}
+            # ---------------- wide variant (C = 256 puts the convs on the tensor-pipe roofline) ----------------
+            if fwd_prec == "bf16":
+                CW = 256
+                sw = 24 * CW + 2 * CW * CW + 42 * CW
+                wide = {}
+                for (bw, tw) in ((1776, 64), (1184, 126)):       # 4 tiles of 256 rows per SM: 3 x 64-frame / 2 x 126-frame windows per tile
+                    torch.manual_seed(0)
+                    wm = b2h.ConvModel(CW, "ReLU", False, precision="bf16").to(dev)
+                    wr = ForwardRunner(wm, bw, tw, n_slots=4, x_dtype=torch.bfloat16)
+                    for s in range(4):
+                        wr.x[s].copy_(synthetic.model_batch(bw, tw, seed=300 + s)["input_kp"])
+                    wr.capture(8)
+                    for _ in range(3):
+                        wr.graph.replay()
+                    torch.cuda.synchronize()
+                    ev0.record()
+                    for _ in range(5):
+                        wr.graph.replay()
+                    ev1.record()
+                    torch.cuda.synchronize()
+                    w_ms = ev0.elapsed_time(ev1) / 40
+                    w_tfl = 2 * (5 * tw - 6) * sw * bw / (w_ms * 1e-3) / 1e12
+                    wide[f"{bw}x{tw}"] = {"value": bw * tw / (w_ms * 1e-3), "unit": "frames/s", "ms_per_batch": w_ms,
+                                          "roofline": {"bound": "tensor", "achieved": w_tfl, "peak": pk["tflops"], "unit": "TFLOP/s",
+                                                       "frac": w_tfl / pk["tflops"]}}
+                    del wr, wm
+                line["fwd_wide"] = {"metric": "body2hand_forward_frames_per_sec", "dtype": "bf16", "conv_channels": CW,
+                                    "workload": "forward, conv_channels=256 (streamed-weight tcgen05 kernel), bf16 inputs, CUDA graph of 8 launches over 4 resident batches",
+                                    "batches": wide, "tc_status": int(lib.b2h_tc_status())}
             # ---------------- K0 preprocessing: 2 h of 30 fps frames ----------------
             F = 216000
             pose, lh, rh = synthetic.synthetic_clip(F, seed=1234)

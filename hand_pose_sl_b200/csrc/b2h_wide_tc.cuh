@@ -264,25 +264,35 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_fwd_kernel(WideA
         acc_phase ^= 1;
         tc_fence_after();
         if (p.dbg && blockIdx.x == 0 && tid == 0 && en < 124) p.dbg[en++] = clock64();   // accumulators complete
-        for (int j = 0; j < 2; ++j) {
-          const RowCtx rc = rowctx(j, tile);
-          const uint32_t taddr = tbase + lane_addr + 256 * j;
-          if (l < 3) {
-            for (int c0 = 32 * ch; c0 < N; c0 += 64) {
-              uint32_t v[32];
-              tmem_ld32(taddr + c0, v);
-              tmem_ld_wait();
+        if (l < 3) {
+          // both 128-row accumulators' chunks are fetched before one wait: two TMEM loads in flight per thread
+          const RowCtx rc0 = rowctx(0, tile), rc1 = rowctx(1, tile);
+          const uint32_t taddr = tbase + lane_addr;
+          for (int c0 = 32 * ch; c0 < N; c0 += 64) {
+            uint32_t v0[32], v1[32];
+            tmem_ld32(taddr + c0, v0);
+            tmem_ld32(taddr + 256 + c0, v1);
+            tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (c0 + 8 * i >= N) continue;        // N is a multiple of 16: never write a chunk past the layer's columns
-                float f[8];
+            for (int i = 0; i < 4; ++i) {
+              if (c0 + 8 * i >= N) continue;          // N is a multiple of 16: never write a chunk past the layer's columns
+              const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[l][c0 + 8 * i]);
+              const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[l][c0 + 8 * i + 4]);
+              const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+              float f0[8], f1[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                  f[q] = rc.valid ? fmaxf(__uint_as_float(v[8 * i + q]) + bias_s[l][c0 + 8 * i + q], 0.0f) : 0.0f;
-                store8_bf16(A, CH, rc.row, (c0 >> 3) + i, f);
+              for (int q = 0; q < 8; ++q) {
+                f0[q] = rc0.valid ? fmaxf(__uint_as_float(v0[8 * i + q]) + bb[q], 0.0f) : 0.0f;
+                f1[q] = rc1.valid ? fmaxf(__uint_as_float(v1[8 * i + q]) + bb[q], 0.0f) : 0.0f;
               }
+              store8_bf16(A, CH, rc0.row, (c0 >> 3) + i, f0);
+              store8_bf16(A, CH, rc1.row, (c0 >> 3) + i, f1);
             }
-          } else {
+          }
+        } else {
+          for (int j = 0; j < 2; ++j) {
+            const RowCtx rc = rowctx(j, tile);
+            const uint32_t taddr = tbase + lane_addr + 256 * j;
             // layer 4: prediction rows (+ mask_output utils.py:309-312, de-normalisation) straight to global memory
             int len = T;
             if (rc.valid && p.lengths) { len = p.lengths[rc.gw]; len = len < 0 ? 0 : (len > T ? T : len); }

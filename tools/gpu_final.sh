@@ -10,6 +10,6 @@ python bench.py --steps 80 --warmup 40 --skip-extras > gpurun_out/plain_bench.lo
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 80 --warmup 40 --skip-extras > gpurun_out/ncu_bench.log 2>&1; echo "ncu launches exit $?" >> gpurun_out/summary.txt
 python tools/prof_target.py 3 > gpurun_out/plain_prof.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:'preprocess_kernel|conv_tc_tile_kernel|adam_kernel' -c 12 \
+ncu --set full --clock-control none --import-source on -k regex:'preprocess_kernel|conv_tc_tile_kernel|conv_tc_wide_fwd_kernel|adam_kernel' -c 15 \
     -o gpurun_out/prof_final -f python tools/prof_target.py 3 > gpurun_out/ncu_prof.log 2>&1; echo "ncu full exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt

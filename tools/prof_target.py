@@ -34,3 +34,11 @@ for _ in range(reps):
     r.step(0)
 torch.cuda.synchronize()
 print("prof_target done, loss", float(r.loss[0]))
+
+# wide variant (conv_channels = 256): streamed-weight forward kernel, 4 tiles per SM
+wm = b2h.ConvModel(256, "ReLU", False, precision="bf16").to(dev)
+wr = ForwardRunner(wm, 1184, 126, x_dtype=torch.bfloat16)
+wr.x[0].copy_(synthetic.model_batch(1184, 126, seed=300)["input_kp"])
+for _ in range(reps):
+    wr.run(0)
+torch.cuda.synchronize()
