@@ -81,6 +81,13 @@ extern "C" int b2h_supported(int T, int n_in, int C, int pos_emb, int precision)
   if (precision == B2H_BF16) return (tc_fwd_supported(g, T) && fp32_smem_bytes(g, T, true) <= (size_t)226 * 1024) ? 1 : 0;
   return 0;
 }
+extern "C" int b2h_forward_supported(int T, int n_in, int C, int pos_emb, int precision) {
+  if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1) return 0;
+  Geo g = make_geo(n_in, C, pos_emb);
+  if (precision == B2H_FP32) return fp32_smem_bytes(g, T, false) <= (size_t)226 * 1024 ? 1 : 0;
+  if (precision == B2H_BF16) return (tc_tile_ok(g, T, false) || tc_fwd_supported(g, T) || tc_wide_supported(g, T)) ? 1 : 0;
+  return 0;
+}
 extern "C" int64_t b2h_workspace_bytes(int B, int T, int n_in, int C, int pos_emb, int precision) {
   if (!geo_ok(n_in, C, pos_emb, "b2h_workspace_bytes")) return B2H_ESHAPE;
   if (B < 1 || T < 1) return 256;

@@ -59,8 +59,11 @@ int64_t b2h_packed_bytes(int n_in, int C, int pos_emb);
 /* bytes of scratch the train entry points need (per-CTA gradient partials for a deterministic
  * two-stage reduction + loss partials) */
 int64_t b2h_workspace_bytes(int B, int T, int n_in, int C, int pos_emb, int precision);
-/* 1 if (T, C) is supported by the given precision's kernels on this build, else 0 */
+/* 1 if (T, C) is supported by the given precision's kernels (forward AND training) on this build, else 0 */
 int b2h_supported(int T, int n_in, int C, int pos_emb, int precision);
+/* 1 if b2h_conv_forward alone covers (T, C) in the given precision -- wider than b2h_supported: bf16 inference runs
+ * conv_channels up to 256 (streamed-weight tensor-core kernel) -- else 0 */
+int b2h_forward_supported(int T, int n_in, int C, int pos_emb, int precision);
 
 /* Re-layout the flat fp32 parameters into the packed buffer (run after load_state_dict / any
  * out-of-band weight change; the fused Adam keeps it fresh by itself). */

@@ -46,6 +46,14 @@ def test_geometry_queries():
     assert lib.b2h_supported(64, 24, 30, 0, _lib.FP32) == 1
     assert lib.b2h_supported(64, 24, 30, 0, _lib.BF16) == 1
     assert lib.b2h_supported(100000, 24, 30, 0, _lib.FP32) == 0
+    # forward-only coverage is wider: bf16 inference runs conv_channels up to 256 and windows up to 1024 frames
+    assert lib.b2h_forward_supported(64, 24, 256, 0, _lib.BF16) == 1
+    assert lib.b2h_forward_supported(200, 24, 256, 0, _lib.BF16) == 1
+    assert lib.b2h_forward_supported(200, 24, 30, 0, _lib.BF16) == 1
+    assert lib.b2h_forward_supported(1000, 24, 30, 0, _lib.BF16) == 1
+    assert lib.b2h_forward_supported(1000, 24, 256, 0, _lib.BF16) == 0
+    assert lib.b2h_supported(64, 24, 256, 0, _lib.BF16) == 0          # no tensor-core / FFMA training at C = 256
+    assert lib.b2h_forward_supported(64, 24, 256, 0, _lib.FP32) == 1
 
 
 def test_null_and_bad_arguments_return_error_codes():
