@@ -97,6 +97,23 @@ def cpu_reference_arm(steps, warmup, budget_s=25.0):
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
+    # also the "loops vectorised" variant (closed-form masked L1, one multiply for mask_output), so the
+    # reader can see how much of the CPU number is the reference's per-sample Python loops
+    vec_ms = None
+    try:
+        lens = torch.as_tensor(batch["n_frames"], dtype=torch.int64)
+        keep = (torch.arange(T)[None, :] < lens[:, None]).float()[:, :, None, None]
+        n_vec = max(3, min(done, 40))
+        t1 = time.perf_counter()
+        for _ in range(n_vec):
+            pred = oracle.conv_model_forward(st.params, batch["input_kp"], st.pos_emb) * keep
+            loss = oracle.masked_pose_l1_closed_form(pred, batch["target_kp"], batch["n_frames"])
+            st.opt.zero_grad()
+            loss.backward()
+            st.opt.step()
+        vec_ms = (time.perf_counter() - t1) / n_vec * 1e3
+    except Exception:
+        vec_ms = None
     model = ""
     try:
         for line in open("/proc/cpuinfo"):
@@ -107,7 +124,9 @@ def cpu_reference_arm(steps, warmup, budget_s=25.0):
         pass
     return {"value": done * B_TRAIN * T / dt, "unit": "frames/s", "cores": cores, "kind": "port",
             "sample": f"{done} train steps of batch {B_TRAIN}x{T} (C={C}, fp32, reference per-sample loss loops) in {dt:.2f} s",
-            "threads": torch.get_num_threads(), "cpu": model, "ms_per_step": dt / done * 1e3}, done, dt
+            "threads": torch.get_num_threads(), "cpu": model, "ms_per_step": dt / done * 1e3,
+            "ms_per_step_loops_vectorised": vec_ms,
+            "value_loops_vectorised": (B_TRAIN * T / (vec_ms * 1e-3)) if vec_ms else None}, done, dt
 
 
 def run_reference(args, rank):
@@ -427,6 +446,33 @@ def main():
                                                      "window_frames_per_sec": Wn * T / (s_ms * 1e-3)}
         # ---------------- CPU baseline (reference path on this box's host cores) ----------------
         line["cpu_baseline"], _, _ = cpu_reference_arm(200, 2, budget_s=15.0)
+        if not args.skip_extras:
+            # ---------------- launch-latency floor: 40 dependent one-block kernels per graph replay ----------------
+            # Last on purpose and fully guarded: nothing measured above can be affected by it.
+            try:
+                tiny = torch.zeros((1, 1, 21, 2), dtype=torch.float32, device=dev)
+                tlen = torch.ones(1, dtype=torch.int32, device=dev)
+                from hand_pose_sl_b200 import _lib as _l
+
+                def _tiny():
+                    _l.check(lib.b2h_mask_output(_l.ptr(tiny), _l.ptr(tlen), 1, 1, 42, _l.stream_ptr(dev)))
+                _tiny()
+                torch.cuda.synchronize()
+                fg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(fg):
+                    for _ in range(40):
+                        _tiny()
+                fg.replay()
+                torch.cuda.synchronize()
+                ev0.record()
+                for _ in range(10):
+                    fg.replay()
+                ev1.record()
+                torch.cuda.synchronize()
+                line["launch_floor_us"] = ev0.elapsed_time(ev1) * 1e3 / 400
+            except Exception as e:   # noqa: BLE001
+                line["launch_floor_us"] = None
+                line["launch_floor_error"] = str(e)[:200]
 
     sys.stdout.flush()
     try:                                   # NCCL's banner sits in the C stdio buffer: push it to the redirected fd first
