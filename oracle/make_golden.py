@@ -150,6 +150,27 @@ def golden_windowing(name="windowing.npz"):
     print(name, len(cases))
 
 
+def golden_wide(C=256, B=2, T=64, name="convmodel_c256_fwd.npz"):
+    """Wide variant (`--conv-channels 256`): forward only, and only the reference's OUTPUTS are stored -- the 740 650
+    weights are the reference's default init right after torch.manual_seed(0), which oracle.init_params(C, seed=0)
+    reproduces; per-tensor checksums pin that."""
+    M, U, _ = ref_loader.load()
+    torch.manual_seed(0)
+    net = M.ConvModel(C, "ReLU", False)
+    batch = synthetic.model_batch(B, T, seed=4321, ragged=True)
+    x, lengths = batch["input_kp"], batch["n_frames"]
+    out = {"lengths": lengths.numpy(), "input_kp": x.numpy(), "C": np.int64(C), "seed": np.int64(0)}
+    for k, v in net.state_dict().items():
+        out["sum_" + k.replace(".", "_")] = np.float64(v.double().sum().item())
+        out["abssum_" + k.replace(".", "_")] = np.float64(v.double().abs().sum().item())
+    with torch.no_grad():
+        pred = net(x)
+        out["pred"] = pred.contiguous().numpy().copy()
+        out["pred_masked"] = U.mask_output(pred.clone(), lengths).contiguous().numpy().copy()
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, out["pred"].shape, float(np.abs(out["pred"]).max()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)          # deterministic summation order in the fixtures
@@ -158,5 +179,6 @@ if __name__ == "__main__":
     golden_model(64, 2, 64, False, "convmodel_c64.npz", steps=2)
     golden_model(30, 1, 64, False, "convmodel_c30_b1.npz", steps=1)
     golden_model(30, 3, 200, False, "convmodel_c30_t200.npz", steps=1)
+    golden_wide()
     golden_preprocess()
     golden_windowing()

@@ -84,6 +84,21 @@ def test_wide_forward_vs_oracle(B, T, C):
         assert float(ym[i, int(lens[i]):].abs().max() if int(lens[i]) < T else 0.0) == 0.0
 
 
+def test_wide_forward_golden():
+    """conv_channels = 256 against the reference's own outputs (tests/golden/convmodel_c256_fwd.npz; the weights are
+    the reference's seeded default init, reproduced by oracle.init_params and pinned by checksums on the CPU tier)."""
+    g = load_golden("convmodel_c256_fwd.npz")
+    sd = oracle.init_params(int(g["C"]), False, seed=int(g["seed"]))
+    m = _model(sd, int(g["C"]), False, "bf16")
+    x = torch.from_numpy(g["input_kp"]).to(DEV)
+    with torch.no_grad():
+        y = m(x)
+        ym = m.predict(x, lengths=torch.from_numpy(g["lengths"]))
+    _tc_clean()
+    assert oracle.rel_err(y.cpu().numpy(), g["pred"]) <= TOL["bf16"]
+    assert oracle.rel_err(ym.cpu().numpy(), g["pred_masked"]) <= TOL["bf16"]
+
+
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
 def test_bf16_input_tensor(prec):
     sd = oracle.init_params(30, False, seed=0)

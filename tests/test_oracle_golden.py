@@ -29,6 +29,23 @@ def test_forward_matches_reference(name):
         assert not masked[i, int(ln):].any()
 
 
+def test_wide_forward_matches_reference():
+    """conv_channels = 256: the fixture stores only the reference's outputs; the weights are the reference's default
+    init after torch.manual_seed(0), which oracle.init_params reproduces (per-tensor checksums in the fixture)."""
+    g = load_golden("convmodel_c256_fwd.npz")
+    sd = oracle.init_params(int(g["C"]), False, seed=int(g["seed"]))
+    for k, v in sd.items():
+        kk = k.replace(".", "_")
+        assert abs(v.double().sum().item() - float(g["sum_" + kk])) <= 1e-9 * float(g["abssum_" + kk]), k
+        assert abs(v.double().abs().sum().item() - float(g["abssum_" + kk])) <= 1e-9 * float(g["abssum_" + kk]), k
+    x = torch.from_numpy(g["input_kp"])
+    y = oracle.conv_model_forward(sd, x).contiguous()
+    assert oracle.rel_err(y.numpy(), g["pred"]) < 5e-6
+    masked = oracle.mask_output(y.clone(), g["lengths"]).numpy()
+    assert oracle.rel_err(masked, g["pred_masked"]) < 5e-6
+    assert oracle.rel_err(oracle.conv_model_forward_f64(sd, x.numpy()), g["pred"]) < 1e-5
+
+
 @pytest.mark.parametrize("name", MODEL_FIXTURES)
 @pytest.mark.parametrize("kind", ["L1", "confL1"])
 def test_train_steps_match_reference(name, kind):
