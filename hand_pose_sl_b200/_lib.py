@@ -31,6 +31,7 @@ _SIGNATURES = {
     "b2h_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "b2h_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "b2h_forward_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
+    "b2h_kernel_choice": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "b2h_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2h_preprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

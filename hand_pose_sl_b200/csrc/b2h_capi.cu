@@ -38,6 +38,16 @@ static bool geo_ok(int n_in, int C, int pos_emb, const char* who) {
 
 static bool use_tc_train(const Geo& g, int T, int precision) { return precision == B2H_BF16 && tc_tile_ok(g, T, true); }
 
+// Which kernel b2h_conv_forward launches (the ONE place that decides; b2h_kernel_choice reports it).
+static int forward_choice(const Geo& g, int T, int precision) {
+  if (precision == B2H_FP32) return fp32_smem_bytes(g, T, false) <= (size_t)226 * 1024 ? B2H_KERNEL_FFMA : B2H_KERNEL_NONE;
+  if (precision != B2H_BF16) return B2H_KERNEL_NONE;
+  if (tc_tile_ok(g, T, false)) return B2H_KERNEL_TC_TILE;        // independent 128/256-row tiles (T <= 256, C <= 64)
+  if (tc_fwd_supported(g, T)) return B2H_KERNEL_TC_ROWSPACE;     // long windows (T <= 1024, C <= 64): layer-major row space
+  if (tc_wide_supported(g, T)) return B2H_KERNEL_TC_WIDE;        // wide models (C <= 256, T <= 256): streamed weights
+  return B2H_KERNEL_NONE;
+}
+
 static int train_nparts(const Geo& g, int B, int T, int precision) {
   return use_tc_train(g, T, precision) ? tc_train_grid(g, B, T) : fp32_train_grid(g, B, T);
 }
@@ -83,10 +93,15 @@ extern "C" int b2h_supported(int T, int n_in, int C, int pos_emb, int precision)
 }
 extern "C" int b2h_forward_supported(int T, int n_in, int C, int pos_emb, int precision) {
   if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1) return 0;
+  return forward_choice(make_geo(n_in, C, pos_emb), T, precision) != B2H_KERNEL_NONE ? 1 : 0;
+}
+extern "C" int b2h_kernel_choice(int T, int n_in, int C, int pos_emb, int precision, int train) {
+  if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1) return B2H_KERNEL_NONE;
   Geo g = make_geo(n_in, C, pos_emb);
-  if (precision == B2H_FP32) return fp32_smem_bytes(g, T, false) <= (size_t)226 * 1024 ? 1 : 0;
-  if (precision == B2H_BF16) return (tc_tile_ok(g, T, false) || tc_fwd_supported(g, T) || tc_wide_supported(g, T)) ? 1 : 0;
-  return 0;
+  if (!train) return forward_choice(g, T, precision);
+  if (precision != B2H_FP32 && precision != B2H_BF16) return B2H_KERNEL_NONE;
+  if (use_tc_train(g, T, precision)) return B2H_KERNEL_TC_TILE;
+  return fp32_smem_bytes(g, T, true) <= (size_t)226 * 1024 ? B2H_KERNEL_FFMA : B2H_KERNEL_NONE;
 }
 extern "C" int64_t b2h_workspace_bytes(int B, int T, int n_in, int C, int pos_emb, int precision) {
   if (!geo_ok(n_in, C, pos_emb, "b2h_workspace_bytes")) return B2H_ESHAPE;
@@ -122,13 +137,14 @@ extern "C" int b2h_conv_forward(const void* x, int x_dtype, const float* params,
     a.y = y; a.B = B; a.T = T; a.apply_mask = apply_mask; a.mode = 0; a.out_scale = out_scale; a.geo = g;
     return launch_fp32(a, false, (cudaStream_t)stream, 0);
   } else if (precision == B2H_BF16) {
-    if (tc_tile_ok(g, T, false))   // independent 128/256-row tiles (T <= 256): persistent tile kernel
+    const int choice = forward_choice(g, T, precision);
+    if (choice == B2H_KERNEL_TC_TILE)
       return launch_tc_tile_fwd(x, x_dtype, params, reinterpret_cast<const char*>(packed), lengths, y, B, T, apply_mask, out_scale, g,
                                 (cudaStream_t)stream);
-    if (!tc_fwd_supported(g, T) && tc_wide_supported(g, T))   // wide models (C <= 256): weights streamed through smem
+    if (choice == B2H_KERNEL_TC_WIDE)
       return launch_tc_wide_fwd(x, x_dtype, params, reinterpret_cast<const char*>(packed), lengths, y, B, T, apply_mask, out_scale, g,
                                 (cudaStream_t)stream);
-    TcFwdArgs a{};                 // long windows: layer-major row-space kernel
+    TcFwdArgs a{};                 // long windows: layer-major row-space kernel (reports the limits itself when unsupported)
     a.x = x; a.x_dtype = x_dtype; a.params = params; a.packed = reinterpret_cast<const char*>(packed); a.lengths = lengths;
     a.y = y; a.B = B; a.T = T; a.apply_mask = apply_mask; a.out_scale = out_scale; a.geo = g;
     return launch_tc_fwd(a, (cudaStream_t)stream);

@@ -64,6 +64,14 @@ int b2h_supported(int T, int n_in, int C, int pos_emb, int precision);
 /* 1 if b2h_conv_forward alone covers (T, C) in the given precision -- wider than b2h_supported: bf16 inference runs
  * conv_channels up to 256 (streamed-weight tensor-core kernel) -- else 0 */
 int b2h_forward_supported(int T, int n_in, int C, int pos_emb, int precision);
+/* Which kernel the forward (train = 0) or the train step (train = 1) runs for this shape -- the dispatch itself uses
+ * this function, so a test can pin "the tensor-core path is the one that runs" without a GPU. */
+#define B2H_KERNEL_NONE 0        /* unsupported: the entry point returns B2H_ESHAPE */
+#define B2H_KERNEL_FFMA 1        /* fp32-accumulate FFMA kernel (fp32 mode; bf16-mode training beyond the tile kernel) */
+#define B2H_KERNEL_TC_TILE 2     /* tcgen05 tile kernel, weights resident in shared memory (C <= 64 fwd / 32 train, T <= 256) */
+#define B2H_KERNEL_TC_ROWSPACE 3 /* tcgen05 layer-major row-space forward (C <= 64, T <= 1024) */
+#define B2H_KERNEL_TC_WIDE 4     /* tcgen05 streamed-weight forward (C <= 256, T <= 256) */
+int b2h_kernel_choice(int T, int n_in, int C, int pos_emb, int precision, int train);
 
 /* Re-layout the flat fp32 parameters into the packed buffer (run after load_state_dict / any
  * out-of-band weight change; the fused Adam keeps it fresh by itself). */

@@ -56,6 +56,33 @@ def test_geometry_queries():
     assert lib.b2h_forward_supported(64, 24, 256, 0, _lib.FP32) == 1
 
 
+def test_kernel_choice_pins_the_tensor_core_paths():
+    """The dispatch of b2h_conv_forward / the train entry points goes through b2h_kernel_choice: in bf16 mode every
+    BASELINE config, the reference default crop (200 frames) and the wide variant run tcgen05 kernels -- no silent
+    FFMA fallback -- and fp32 mode is always the FFMA kernel."""
+    lib = _lib.load()
+    NONE, FFMA, TILE, ROWSPACE, WIDE = 0, 1, 2, 3, 4
+    fwd = lambda T, C, prec, pe=0: lib.b2h_kernel_choice(T, 24, C, pe, prec, 0)
+    trn = lambda T, C, prec, pe=0: lib.b2h_kernel_choice(T, 24, C, pe, prec, 1)
+    for T in (1, 9, 64, 100, 126, 128, 129, 200, 256):
+        assert fwd(T, 30, _lib.BF16) == TILE and trn(T, 30, _lib.BF16) == TILE, T
+        assert fwd(T, 30, _lib.FP32) == FFMA and trn(T, 30, _lib.FP32) == FFMA, T
+    assert fwd(100, 30, _lib.BF16, 1) == TILE and trn(100, 30, _lib.BF16, 1) == TILE        # pos_emb: 25 input channels
+    assert fwd(64, 64, _lib.BF16) == TILE and trn(64, 64, _lib.BF16) == FFMA                # C > 32 trains on FFMA
+    assert fwd(200, 64, _lib.BF16) == ROWSPACE                                              # tile does not fit smem
+    assert fwd(257, 30, _lib.BF16) == ROWSPACE and fwd(1000, 30, _lib.BF16) == ROWSPACE
+    assert trn(257, 30, _lib.BF16) == FFMA
+    for C in (80, 96, 128, 256):
+        for T in (64, 126, 200, 256):
+            assert fwd(T, C, _lib.BF16) == WIDE, (T, C)
+    assert fwd(300, 256, _lib.BF16) == NONE and fwd(2000, 30, _lib.BF16) == NONE
+    assert trn(64, 256, _lib.BF16) == NONE and trn(64, 256, _lib.FP32) == NONE              # 396 KB of activations
+    assert fwd(64, 256, _lib.FP32) == FFMA
+    assert lib.b2h_kernel_choice(64, 24, 30, 0, 7, 0) == NONE                                # bad precision
+    for T, C in ((64, 30), (200, 30), (64, 256), (300, 256)):
+        assert lib.b2h_forward_supported(T, 24, C, 0, _lib.BF16) == int(fwd(T, C, _lib.BF16) != NONE)
+
+
 def test_null_and_bad_arguments_return_error_codes():
     lib = _lib.load()
     assert lib.b2h_conv_forward(None, 0, None, None, None, None, 1, 64, 24, 30, 0, 0, 0, 1.0, None) == -1
