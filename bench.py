@@ -374,9 +374,12 @@ def main():
                     torch.cuda.synchronize()
                     w_ms = ev0.elapsed_time(ev1) / 40
                     w_tfl = 2 * (5 * tw - 6) * sw * bw / (w_ms * 1e-3) / 1e12
+                    w_traffic = None
+                    if (bw, tw) == (1184, 126) and os.path.isfile(tpath):
+                        w_traffic = json.load(open(tpath)).get("wide_fwd_dram_bytes_per_launch")
                     wide[f"{bw}x{tw}"] = {"value": bw * tw / (w_ms * 1e-3), "unit": "frames/s", "ms_per_batch": w_ms,
                                           "roofline": {"bound": "tensor", "achieved": w_tfl, "peak": pk["tflops"], "unit": "TFLOP/s",
-                                                       "frac": w_tfl / pk["tflops"]}}
+                                                       "frac": w_tfl / pk["tflops"], "traffic": w_traffic}}
                     del wr, wm
                 line["fwd_wide"] = {"metric": "body2hand_forward_frames_per_sec", "dtype": "bf16", "conv_channels": CW,
                                     "workload": "forward, conv_channels=256 (streamed-weight tcgen05 kernel), bf16 inputs, CUDA graph of 8 launches over 4 resident batches",
