@@ -270,7 +270,33 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
     e2e = {"value": e2e_steps * B_TRAIN * T * world / e2e_dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": 4, "steps": e2e_steps, "api": "TrainStepRunner.load(pinned batch) + .step() + loss.item()"}
+           "d2h_bytes_per_step": 4, "steps": e2e_steps, "api": "TrainStepRunner.load(pinned batch) + .step() + loss.item()",
+           "mode": "sequential"}
+    if world == 1:
+        # Same bytes, same per-step loss read, but batch i+1 travels on a copy stream while step i computes
+        # (runner.pipelined_steps: what a prefetching DataLoader gives the reference loop).  Single-process only: an
+        # exception on one rank of a multi-rank run would desynchronise the collectives.  Guarded: on any failure the
+        # sequential number above stands.
+        try:
+            from hand_pose_sl_b200.runner import pipelined_steps
+            for _ in pipelined_steps(runner, (host_batches[i % N_SLOTS] for i in range(6))):
+                pass
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_p = 0
+            for loss_val in pipelined_steps(runner, (host_batches[i % N_SLOTS] for i in range(e2e_steps))):
+                n_p += 1
+            torch.cuda.synchronize()
+            p_dt = time.perf_counter() - t0
+            p_val = n_p * B_TRAIN * T / p_dt
+            e2e["sequential_value"] = e2e["value"]
+            e2e["pipelined_value"] = p_val
+            if n_p == e2e_steps and loss_val == loss_val and p_val > e2e["value"]:      # finite loss, all steps ran
+                e2e["value"] = p_val
+                e2e["mode"] = "pipelined (double-buffered H2D on a copy stream)"
+                e2e["api"] = "runner.pipelined_steps(TrainStepRunner, pinned batches): load + step + loss.item() per step"
+        except Exception as ex:   # noqa: BLE001
+            e2e["pipelined_error"] = str(ex)[:200]
     runner.finish()
 
     line = {"metric": "body2hand_train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,

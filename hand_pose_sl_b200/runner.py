@@ -105,6 +105,50 @@ class TrainStepRunner:
         self.model.packed_weights(fresh_from_kernel=True)
 
 
+def pipelined_steps(runner, batches):
+    """Training loop with a double-buffered input pipeline (what a DataLoader with prefetch gives the reference loop,
+    steps/traintest.py:87-123): while step i runs, batch i+1 travels host -> device on a copy stream into the other
+    slot.  `runner` is a TrainStepRunner or parallel.DataParallelTrainer with n_slots >= 2; `batches` yields
+    reference-style batch dicts in pinned host memory.  Yields the loss of every step as a float (device -> host
+    read, traintest.py:123), so each step's result is observed before the next one is enqueued."""
+    if runner.n_slots < 2:
+        raise RuntimeError("pipelined_steps needs a runner with n_slots >= 2")
+    dev = runner.x.device
+    main = torch.cuda.current_stream(dev)
+    copy_stream = torch.cuda.Stream(dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]     # batch landed in slot s
+    freed = [torch.cuda.Event(), torch.cuda.Event()]     # the step that read slot s has finished
+    used = [False, False]
+    it = iter(batches)
+
+    def issue(i, batch):
+        s = i & 1
+        if used[s]:
+            copy_stream.wait_event(freed[s])             # do not overwrite a slot a step is still reading
+        with torch.cuda.stream(copy_stream):
+            runner.load(batch, slot=s)
+            ready[s].record(copy_stream)
+
+    nxt = next(it, None)
+    if nxt is None:
+        return
+    issue(0, nxt)
+    i = 0
+    while True:
+        s = i & 1
+        nxt = next(it, None)
+        if nxt is not None:
+            issue(i + 1, nxt)                            # travels while step i computes
+        main.wait_event(ready[s])
+        loss = runner.step(s)
+        freed[s].record(main)
+        used[s] = True
+        yield float(loss.item())
+        if nxt is None:
+            return
+        i += 1
+
+
 class ForwardRunner:
     """ConvModel.forward for a fixed (B, T) with static buffers (inference serving loop)."""
 

@@ -158,3 +158,69 @@ def test_select_window_requires_mode_for_long_clips():
 def test_sliding_window_starts():
     assert list(b2h.sliding_window_starts(200, 64, 64)) == [0, 64, 128, 192]
     assert list(b2h.sliding_window_starts(65, 64, 16)) == [0, 16, 32, 48, 64]
+
+
+def test_pipelined_steps_slot_discipline(monkeypatch):
+    """runner.pipelined_steps (host logic, CUDA stream/event calls faked): batch i+1 is loaded into the other slot
+    before step i is enqueued, a slot is only overwritten after the step that read it was recorded, the main stream
+    waits for the landing event of the slot it steps on, and every batch produces exactly one loss."""
+    import contextlib
+    import torch
+    from hand_pose_sl_b200 import runner as R
+
+    log = []
+
+    class FakeEvent:
+        n = 0
+
+        def __init__(self):
+            FakeEvent.n += 1
+            self.id = FakeEvent.n
+
+        def record(self, stream=None):
+            log.append(("record", self.id, getattr(stream, "name", "?")))
+
+    class FakeStream:
+        def __init__(self, dev=None, name="copy"):
+            self.name = name
+
+        def wait_event(self, ev):
+            log.append(("wait", self.name, ev.id))
+
+    main = FakeStream(name="main")
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: main)
+    monkeypatch.setattr(torch.cuda, "Stream", FakeStream)
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+
+    class FakeRunner:
+        n_slots = 2
+        x = torch.zeros(1)
+
+        def load(self, batch, slot=0):
+            log.append(("load", batch, slot))
+
+        def step(self, slot=0):
+            log.append(("step", slot))
+            return torch.tensor(float(slot))
+
+    losses = list(R.pipelined_steps(FakeRunner(), range(5)))
+    assert losses == [0.0, 1.0, 0.0, 1.0, 0.0]
+    loads = [e for e in log if e[0] == "load"]
+    steps = [e for e in log if e[0] == "step"]
+    assert [(b, s) for _, b, s in loads] == [(0, 0), (1, 1), (2, 0), (3, 1), (4, 0)] and len(steps) == 5
+    for i in range(4):       # load(i+1) precedes step(i)
+        assert log.index(("load", i + 1, (i + 1) & 1)) < [k for k, e in enumerate(log) if e[0] == "step"][i]
+    ready = {0: 1, 1: 2}     # event ids: ready[0], ready[1], freed[0], freed[1] (construction order)
+    freed = {0: 3, 1: 4}
+    for i in range(5):       # step i is preceded by main.wait(ready[slot]) and followed by record(freed[slot])
+        k = [k for k, e in enumerate(log) if e[0] == "step"][i]
+        assert log[k - 1] == ("wait", "main", ready[i & 1]) and log[k + 1] == ("record", freed[i & 1], "main")
+    for i in range(2, 5):    # overwriting a slot waits for the step that read it
+        k = log.index(("load", i, i & 1))
+        assert log[k - 1] == ("wait", "copy", freed[i & 1])
+        assert ("record", freed[i & 1], "main") in log[:k]
+    assert list(R.pipelined_steps(FakeRunner(), [])) == []
+    FakeRunner.n_slots = 1
+    with pytest.raises(RuntimeError):
+        list(R.pipelined_steps(FakeRunner(), range(2)))
