@@ -171,6 +171,22 @@ def golden_wide(C=256, B=2, T=64, name="convmodel_c256_fwd.npz"):
     print(name, out["pred"].shape, float(np.abs(out["pred"]).max()))
 
 
+def golden_writers(name="writers.npz"):
+    """Inference writers: array2open_pose (steps/utils.py:355-364), order_and_reshape_toh5
+    (steps/traintest.py:302-317), L12Pixels (steps/utils.py:291-299) executed from the reference on a seeded prediction."""
+    _, U, _ = ref_loader.load()
+    to_h5 = ref_loader.load_function("steps/traintest.py", "order_and_reshape_toh5")
+    g = torch.Generator().manual_seed(99)
+    pred = (torch.rand((7, 21, 2), generator=g) * 1280.0).float()
+    out = {"pred": pred.numpy(),
+           "openpose": np.asarray([U.array2open_pose(pred[t].numpy()) for t in range(pred.shape[0])], dtype=np.float64),
+           "h5": np.asarray(to_h5(pred)),
+           "l1": np.float64(0.0123), "l1_pixels_21": np.float64(U.L12Pixels(21, 1280)(0.0123)),
+           "l1_pixels_4": np.float64(U.L12Pixels(4, 1280)(0.0123))}
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(name, out["openpose"].shape, out["h5"].shape, out["h5"].dtype)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)          # deterministic summation order in the fixtures
@@ -180,5 +196,6 @@ if __name__ == "__main__":
     golden_model(30, 1, 64, False, "convmodel_c30_b1.npz", steps=1)
     golden_model(30, 3, 200, False, "convmodel_c30_t200.npz", steps=1)
     golden_wide()
+    golden_writers()
     golden_preprocess()
     golden_windowing()

@@ -81,3 +81,22 @@ def load():
         _cache["utils"] = _load("b2h_ref_steps_utils", "steps/utils.py")
         _cache["data"] = _load("b2h_ref_text_pose_dataset", "dataloaders/text_pose_dataset.py")
     return _cache["models"], _cache["utils"], _cache["data"]
+
+
+def load_function(rel_path, name):
+    """One top-level function of a reference file that cannot be imported as a module (steps/traintest.py uses
+    package-relative imports and h5py): its source is taken UNMODIFIED from the file and executed with numpy / torch
+    in scope.  TEST INFRASTRUCTURE ONLY."""
+    import ast
+    import numpy as np
+    import torch
+    if not available():
+        raise FileNotFoundError(f"reference not mounted at {REF_ROOT}")
+    path = os.path.join(REF_ROOT, "body2hand", "src", rel_path)
+    src = open(path).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            ns = {"np": np, "torch": torch}
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+            return ns[name]
+    raise KeyError(f"{name} not found in {path}")

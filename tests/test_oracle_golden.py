@@ -127,3 +127,14 @@ def test_adam_written_out_matches_torch():
         opt.step()
         q, m, v = oracle.adam_reference_step(q, g1 * step, m, v, step)
     assert np.allclose(q, tp.detach().numpy(), rtol=0, atol=1e-12)
+
+
+def test_writers_match_reference():
+    """the writer layouts and the loss-to-pixels scalar against outputs of the reference's own functions."""
+    g = load_golden("writers.npz")
+    pred = g["pred"]
+    for t in range(pred.shape[0]):
+        assert np.array_equal(oracle.array2open_pose(pred[t]).astype(np.float64), g["openpose"][t])
+    assert np.array_equal(oracle.order_and_reshape_toh5(pred), g["h5"])
+    assert oracle.l1_to_pixels(float(g["l1"]), 21, 1280) == float(g["l1_pixels_21"])
+    assert oracle.l1_to_pixels(float(g["l1"]), 4, 1280) == float(g["l1_pixels_4"])

@@ -42,3 +42,15 @@ def test_transforms_live():
     assert np.array_equal(item["input_kp"].numpy(), out["input_kp"][0])
     assert np.array_equal(item["target_kp"].numpy(), out["target_kp"][0])
     assert np.array_equal(item["left_hand_kp"].numpy(), out["left_hand_kp"][0])
+
+
+def test_writers_live():
+    """array2open_pose / L12Pixels from steps/utils.py and order_and_reshape_toh5 from steps/traintest.py (taken from
+    the file unmodified: the module itself needs h5py and package-relative imports)."""
+    _, U, _ = ref_loader.load()
+    to_h5 = ref_loader.load_function("steps/traintest.py", "order_and_reshape_toh5")
+    pred = (torch.rand((5, 21, 2), generator=torch.Generator().manual_seed(3)) * 1280.0).float()
+    for t in range(5):
+        assert np.array_equal(np.asarray(U.array2open_pose(pred[t].numpy())), oracle.array2open_pose(pred[t].numpy()).astype(np.float64))
+    assert np.array_equal(to_h5(pred), oracle.order_and_reshape_toh5(pred.numpy()))
+    assert U.L12Pixels(21, 1280)(0.5) == oracle.l1_to_pixels(0.5, 21, 1280)
