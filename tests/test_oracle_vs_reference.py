@@ -54,3 +54,16 @@ def test_writers_live():
         assert np.array_equal(np.asarray(U.array2open_pose(pred[t].numpy())), oracle.array2open_pose(pred[t].numpy()).astype(np.float64))
     assert np.array_equal(to_h5(pred), oracle.order_and_reshape_toh5(pred.numpy()))
     assert U.L12Pixels(21, 1280)(0.5) == oracle.l1_to_pixels(0.5, 21, 1280)
+
+
+def test_host_scalars_live():
+    """The host-side mirrors (a17): adjust_learning_rate (steps/utils.py:301-307) and L12Pixels (:291-299)."""
+    import hand_pose_sl_b200 as b2h
+    _, U, _ = ref_loader.load()
+    w = torch.nn.Parameter(torch.zeros(3))
+    for epoch in (0, 1, 7, 30):
+        o_ref, o_mine = torch.optim.Adam([w], lr=1.0), torch.optim.Adam([w], lr=1.0)
+        assert U.adjust_learning_rate(2e-4, 10, o_ref, epoch) == b2h.adjust_learning_rate(2e-4, 10, o_mine, epoch)
+        assert o_ref.param_groups[0]["lr"] == o_mine.param_groups[0]["lr"]
+    for joints in (4, 12, 21):
+        assert U.L12Pixels(joints, 1280)(0.0371) == b2h.L12Pixels(joints, 1280)(0.0371)
