@@ -9,7 +9,9 @@ from .steps import (FusedAdam, L12Pixels, adjust_learning_rate, forward_backward
 from .datasets import GpuPoseDataset, PackedClips, pack_metadata, split_metadata  # noqa: F401
 from .transforms import BODY_HEAD_KEYPOINTS, PreprocessRightHand, select_window, sliding_window_starts  # noqa: F401
 
-__all__ = ["ConvModel", "LinearPositionalEmbedding", "maskedPoseL1", "poderatedPoseL1", "mask_output", "FusedAdam",
+fused_step = fused_train_step      # the name SURVEY.md 8b uses for the optional one-call fast path
+
+__all__ = ["fused_step", "ConvModel", "LinearPositionalEmbedding", "maskedPoseL1", "poderatedPoseL1", "mask_output", "FusedAdam",
            "fused_train_step", "forward_backward", "validate_batch", "PreprocessRightHand", "select_window",
            "sliding_window_starts", "L12Pixels", "adjust_learning_rate", "BODY_HEAD_KEYPOINTS", "GpuPoseDataset", "PackedClips",
            "pack_metadata", "split_metadata", "format_prediction"]
