@@ -1,0 +1,72 @@
+"""CPU tier: a numpy model of the tensor-core kernels' tiling (b2h_train_tc.cuh / b2h_wide_tc.cuh) against the oracle.
+
+The kernels pack whole windows into a row segment `[2 zero rows][window][2 zero rows][window]...`, compute every conv as
+`out[row 2+m] = bias + sum_k W_k . in[row m+k]` over the WHOLE segment (tap k = +k rows of the operand's start address)
+and zero the rows that are not real frames.  This model executes exactly that arithmetic in float64 with the plans'
+geometry (segment rows MB, windows per segment gh = (MB+2)//(T+2), rows past a window's end invalid) and must reproduce
+the reference forward: shared zero rows really isolate neighbouring windows, for every T and batch tail."""
+import numpy as np
+import pytest
+import torch
+
+import b2h_oracle as oracle
+from hand_pose_sl_b200 import synthetic
+
+
+def plan(T, wide):
+    """(segment rows MB, segments per tile, windows per segment) as tc_tile_plan / launch_tc_wide_fwd choose them."""
+    if wide:
+        return 256, 1, 258 // (T + 2)
+    if T <= 64:
+        return 64, 2, 66 // (T + 2)
+    mb = 256 if T > 128 else 128
+    return mb, 1, (mb + 2) // (T + 2)
+
+
+def tiled_forward(sd, x, wide):
+    B, T = x.shape[:2]
+    MB, nseg, gh = plan(T, wide)
+    assert gh >= 1
+    W = [sd[f"conv{i}.weight"].double().numpy() for i in range(1, 5)]        # (co, ci, k)
+    b = [sd[f"conv{i}.bias"].double().numpy() for i in range(1, 5)]
+    xin = x.reshape(B, T, -1).double().numpy()
+    y = np.zeros((B, T, 42))
+    wpt = nseg * gh
+    for tile in range((B + wpt - 1) // wpt):
+        for h in range(nseg):
+            m = np.arange(MB)
+            wj, t = m // (T + 2), m % (T + 2)
+            gw = tile * wpt + h * gh + wj
+            valid = (t < T) & (wj < gh) & (gw < B)
+            buf = np.zeros((MB + 8, xin.shape[2]))                              # HR = MB + 8 rows, rows 0,1 and the tail stay zero
+            buf[2 + m[valid]] = xin[gw[valid], t[valid]]
+            for l in range(4):
+                out = np.zeros((MB, W[l].shape[0]))
+                for k in range(5):
+                    out += buf[m + k] @ W[l][:, :, k].T                          # output row 2+m reads input row m+k
+                out += b[l]
+                if l < 3:
+                    out = np.maximum(out, 0.0)
+                out[~valid] = 0.0                                               # the epilogue writes zeros on non-frame rows
+                buf = np.zeros((MB + 8, out.shape[1]))
+                buf[2 + m] = out
+            y[gw[valid], t[valid]] = out[valid]
+    return y
+
+
+@pytest.mark.parametrize("B,T,C,wide", [(5, 64, 30, False), (7, 21, 30, False), (3, 9, 16, False), (4, 65, 30, False),
+                                        (3, 126, 30, False), (2, 128, 24, False), (3, 129, 30, False), (2, 200, 30, False),
+                                        (2, 256, 30, False), (7, 64, 48, True), (5, 126, 40, True), (2, 200, 40, True),
+                                        (4, 1, 30, False), (10, 31, 40, True)])
+def test_tiling_reproduces_the_reference_forward(B, T, C, wide):
+    sd = oracle.init_params(C, False, seed=B * 7 + T)
+    x = synthetic.model_batch(B, T, seed=B * 100 + T)["input_kp"]
+    ref = oracle.conv_model_forward_f64(sd, x.numpy())
+    got = tiled_forward(sd, x, wide).reshape(B, T, 21, 2)
+    assert oracle.rel_err(got, ref) < 1e-10
+
+
+def test_windows_per_tile():
+    assert plan(64, False) == (64, 2, 1) and plan(31, False) == (64, 2, 2) and plan(9, False) == (64, 2, 6)
+    assert plan(126, False) == (128, 1, 1) and plan(200, False) == (256, 1, 1)
+    assert plan(64, True) == (256, 1, 3) and plan(126, True) == (256, 1, 2) and plan(200, True) == (256, 1, 1)
