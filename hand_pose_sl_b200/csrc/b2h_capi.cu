@@ -174,6 +174,11 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
     return B2H_EALIGN;
   }
   g = make_geo(n_in, C, pos_emb);
+  if (!use_tc_train(g, T, precision) && fp32_smem_bytes(g, T, true) > (size_t)226 * 1024) {
+    set_error("%s: no training kernel for conv_channels=%d, T=%d (tcgen05 training covers C <= 32 and T <= 256 in bf16 mode; "
+              "the FFMA kernel would need %zu B of shared memory)", who, C, T, fp32_smem_bytes(g, T, true));
+    return B2H_ESHAPE;
+  }
   nparts = train_nparts(g, B, T, precision);
   const int64_t stride = train_part_stride(g, T, precision);
   const int64_t need = ((int64_t)nparts * stride + nparts) * 4 + 64;   // + grid-barrier words of the fused kernel

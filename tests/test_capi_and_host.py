@@ -81,6 +81,13 @@ def test_kernel_choice_pins_the_tensor_core_paths():
     assert lib.b2h_kernel_choice(64, 24, 30, 0, 7, 0) == NONE                                # bad precision
     for T, C in ((64, 30), (200, 30), (64, 256), (300, 256)):
         assert lib.b2h_forward_supported(T, 24, C, 0, _lib.BF16) == int(fwd(T, C, _lib.BF16) != NONE)
+    # a shape without a training kernel is refused with a message that names the limits (no launch is attempted)
+    import ctypes
+    buf = (ctypes.c_char * 4096)()
+    ptr = ctypes.c_void_p((ctypes.addressof(buf) + 255) // 256 * 256)
+    rc = lib.b2h_train_forward_backward(ptr, 0, ptr, None, ptr, ptr, ptr, ptr, ptr, None, 4, 64, 24, 256, 0, _lib.LOSS_L1, _lib.BF16,
+                                        None, ptr, 1 << 20, None)
+    assert rc == -2 and "no training kernel for conv_channels=256" in _lib.last_error()
 
 
 def test_null_and_bad_arguments_return_error_codes():
