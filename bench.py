@@ -26,6 +26,43 @@ FWD_FLOP_PER_WINDOW = 2 * (5 * T - 6) * S_MAC                # 2 373 840 at T=64
 TRAIN_FLOP_PER_WINDOW = 2 * (5 * T - 6) * (3 * S_MAC - 24 * C)   # 6 669 360
 PRE_BYTES_PER_FRAME = 804 + 648                              # K0 figure of record
 N_SLOTS = 40                                                 # resident batches rotated so the working set > L2
+MIN_TIMED_STEPS = 20000                                      # the timed region lasts >= ~0.5 s whatever --steps is
+
+
+def dp_parity_check(b2h, synthetic, DataParallelTrainer, TrainStepRunner, dev, rank, world, prec, exchange, multicast):
+    """SURVEY 8e parity, run inside the N>1 bench because the GPU test box has one GPU: W ranks x 16 windows ==
+    one rank on the concatenated 16*W windows (loss per step, post-step weights), replicas bit-identical."""
+    import torch
+    import torch.distributed as dist
+    from hand_pose_sl_b200 import parallel
+    Bp, Tp, steps = 16, 64, 4
+    batch = synthetic.model_batch(Bp * world, Tp, seed=77, ragged=True)
+    torch.manual_seed(0)
+    m = b2h.ConvModel(C, "ReLU", False, precision=prec).to(dev)
+    o = b2h.FusedAdam(m.parameters(), lr=LR)
+    tr = DataParallelTrainer(m, o, Bp, Tp, "L1", exchange=exchange, multicast=multicast)
+    tr.load(parallel.shard_batch(batch, rank, world), non_blocking=False)
+    losses = [float(parallel.combine_losses(tr.step(0), "L1")) for _ in range(steps)]
+    identical = bool(tr.replicas_identical())
+    tr.finish()
+    flat = m.flat_parameters().clone()
+    out = {"small_run": f"{world} ranks x {Bp} windows x {Tp} frames, {steps} steps, ragged lengths",
+           "replicas_bit_identical": identical}
+    if rank == 0:
+        torch.manual_seed(0)
+        ref = b2h.ConvModel(C, "ReLU", False, precision=prec).to(dev)
+        ro = b2h.FusedAdam(ref.parameters(), lr=LR)
+        rr = TrainStepRunner(ref, ro, Bp * world, Tp, "L1")
+        rr.load(batch, non_blocking=False)
+        rl = [float(rr.step(0)) for _ in range(steps)]
+        rr.finish()
+        rf = ref.flat_parameters()
+        out["loss_rel_err_vs_1rank"] = max(abs(a - b) / abs(b) for a, b in zip(losses, rl))
+        out["weights_max_abs_diff_vs_1rank"] = float((flat - rf).abs().max())
+        out["weights_frac_within_1e-4"] = float(((flat - rf).abs() <= 1e-4 * rf.abs().max()).float().mean())
+        out["weights_bound_2_lr_steps"] = 2 * LR * steps
+    dist.barrier()
+    return out
 
 
 def peaks():
@@ -152,6 +189,7 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
     ap.add_argument("--skip-extras", action="store_true", help="only the headline train-step number")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="multi-GPU gradient exchange")
+    ap.add_argument("--no-multicast", action="store_true", help="p2p exchange: unicast stores even when an NVLS mapping exists")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -178,7 +216,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("B2H_NCCL_DEBUG", "WARN")    # keep stdout to the one JSON line
+        # NCCL_DEBUG is left as the caller set it (its lines go to stderr: fd 1 is redirected below until the JSON line)
         dist.init_process_group("nccl", device_id=dev)
     pk = peaks()
     train_prec = "bf16" if args.precision == "auto" else args.precision
@@ -188,20 +226,29 @@ def main():
     torch.manual_seed(0)
     model = b2h.ConvModel(C, "ReLU", False, precision=train_prec).to(dev)
     opt = b2h.FusedAdam(model.parameters(), lr=LR)
+    # bf16 mode ships input_kp as bf16 (the kernel rounds it to bf16 anyway: bit-identical result, shorter H2D copy)
+    x_dt = torch.bfloat16 if train_prec == "bf16" else torch.float32
     if world > 1:
-        runner = DataParallelTrainer(model, opt, B_TRAIN, T, "L1", n_slots=N_SLOTS, exchange=args.exchange)
+        runner = DataParallelTrainer(model, opt, B_TRAIN, T, "L1", n_slots=N_SLOTS, exchange=args.exchange, x_dtype=x_dt,
+                                     multicast=not args.no_multicast)
     else:
-        runner = TrainStepRunner(model, opt, B_TRAIN, T, "L1", n_slots=N_SLOTS)
-    host_batches = []
+        runner = TrainStepRunner(model, opt, B_TRAIN, T, "L1", n_slots=N_SLOTS, x_dtype=x_dt)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                                       # long before the timed region: nvidia-smi needs ~0.2 s to start
+    staged = []
     for s in range(N_SLOTS):
         b = synthetic.model_batch(B_TRAIN, T, seed=1234 + 1000 * rank + s)
-        host_batches.append({k: v.pin_memory() for k, v in b.items()})
-        runner.load(host_batches[-1], slot=s, non_blocking=False)
+        staged.append(runner.host_stage(b))                   # ONE pinned buffer per batch (x | target | lengths)
+        runner.load_staged(staged[-1], slot=s, non_blocking=False)
     chunk = min(N_SLOTS, args.steps)
+    # The driver's --steps can be as small as 20 (0.6 ms of GPU time): the timed region repeats the K-step unit R times
+    # so that it lasts >= ~0.5 s at any K (clock samples under load, no start-up skew); ms_per_step = region / (K * R).
+    repeats = max(1, -(-MIN_TIMED_STEPS // args.steps))
     graphed = True
     try:
         runner.capture(chunk)
-    except Exception as e:                                    # e.g. NCCL capture refused: direct launches instead
+    except Exception as e:                                    # e.g. capture refused: direct launches instead
         graphed = False
         sys.stderr.write(f"[bench] CUDA graph capture unavailable ({type(e).__name__}: {e}); direct launches\n")
         torch.cuda.synchronize()
@@ -216,18 +263,17 @@ def main():
             runner.step(done % N_SLOTS)
             done += 1
 
-    run_steps(args.warmup)
+    # warm-up: the SAME graph that is timed, at least W steps and at least one full replay
+    run_steps(max(args.warmup, chunk))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record()
-    run_steps(args.steps)
+    run_steps(args.steps)                                     # untimed, not synchronised: the ranks meet inside these steps
+    ev0.record()                                              # ... so every rank's clock starts in lock-step with its peers
+    for _ in range(repeats):
+        run_steps(args.steps)
     ev1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -238,77 +284,88 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    timed_steps = args.steps * repeats
     torch.cuda.synchronize()
     c0 = _lib.launch_count()
     runner.step(0)                                            # count the kernels of ONE step (outside the timed region)
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - c0
-    gpu_launches = args.steps * launches_per_step
-    value = args.steps * B_TRAIN * T * world / (ms * 1e-3)
+    gpu_launches = timed_steps * launches_per_step
+    value = timed_steps * B_TRAIN * T * world / (ms * 1e-3)
     final_loss = float(runner.loss[0].item())
+    tc_status = int(_lib.load().b2h_tc_status())
 
-    # ---------------- e2e: host buffers -> H2D -> step -> D2H loss, every step ----------------
-    e2e_steps = min(args.steps, 100)
-    h2d = sum(host_batches[0][k].numel() * host_batches[0][k].element_size() for k in ("input_kp", "target_kp")) + B_TRAIN * 4
-    lengths32 = [hb["n_frames"].to(torch.int32).pin_memory() for hb in host_batches]
-    for hb, l32 in zip(host_batches, lengths32):
-        hb["n_frames"] = l32
-    for i in range(5):
-        runner.load(host_batches[i % N_SLOTS], slot=0)
-        float(runner.step(0).item())
+    # ---------------- e2e: pinned host buffer -> ONE H2D copy -> step -> D2H loss, every step ----------------
+    # runner.pipelined_steps: batch i+1 travels on a copy stream while step i computes (what a prefetching DataLoader
+    # gives the reference loop); the loss of every step is read back on the host before the next step is enqueued.
+    from hand_pose_sl_b200.runner import pipelined_steps
+    e2e_steps = 200
+    h2d = int(staged[0].numel())
+    for _ in pipelined_steps(runner, (staged[i % N_SLOTS] for i in range(10))):
+        pass
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        runner.load(host_batches[i % N_SLOTS], slot=0)        # pinned host -> device, inside the timed region
-        loss_val = float(runner.step(0).item())               # device -> host read of the step's result
+    n_p, loss_val = 0, float("nan")
+    for loss_val in pipelined_steps(runner, (staged[i % N_SLOTS] for i in range(e2e_steps))):
+        n_p += 1
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
+    # sequential variant (copy, then step, then read) for reference
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(50):
+        runner.load_staged(staged[i % N_SLOTS], slot=0)
+        loss_val = float(runner.step(0).item())
+    torch.cuda.synchronize()
+    seq_dt = (time.perf_counter() - t0) / 50
     if world > 1:
-        t = torch.tensor([e2e_dt], device=dev)
+        t = torch.tensor([e2e_dt, seq_dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
-    e2e = {"value": e2e_steps * B_TRAIN * T * world / e2e_dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": 4, "steps": e2e_steps, "api": "TrainStepRunner.load(pinned batch) + .step() + loss.item()",
-           "mode": "sequential"}
-    if world == 1:
-        # Same bytes, same per-step loss read, but batch i+1 travels on a copy stream while step i computes
-        # (runner.pipelined_steps: what a prefetching DataLoader gives the reference loop).  Single-process only: an
-        # exception on one rank of a multi-rank run would desynchronise the collectives.  Guarded: on any failure the
-        # sequential number above stands.
+        e2e_dt, seq_dt = float(t[0].item()), float(t[1].item())
+    e2e = {"value": n_p * B_TRAIN * T * world / e2e_dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 4, "steps": n_p,
+           "api": "runner.pipelined_steps(runner, runner.host_stage(batch) buffers): ONE cudaMemcpyAsync + step + loss.item() per step",
+           "mode": "pipelined (double-buffered H2D on a copy stream)", "input_dtype": str(x_dt).replace("torch.", ""),
+           "sequential_value": B_TRAIN * T * world / seq_dt, "us_per_step": e2e_dt / max(n_p, 1) * 1e6,
+           "h2d_gbs": h2d / (e2e_dt / max(n_p, 1)) / 1e9}
+
+    # ---------------- data-parallel parity, untimed (the driver's GPU test box has one GPU) ----------------
+    dp_parity = None
+    if world > 1:
+        dp_parity = {"replicas_bit_identical_after_timed_run": bool(runner.replicas_identical()),
+                     "peers_in_exchange_table": int(runner.peers_seen), "exchange": runner.exchange,
+                     "multicast_push": bool(getattr(runner, "mc_ptr", 0))}
         try:
-            from hand_pose_sl_b200.runner import pipelined_steps
-            for _ in pipelined_steps(runner, (host_batches[i % N_SLOTS] for i in range(6))):
-                pass
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            n_p = 0
-            for loss_val in pipelined_steps(runner, (host_batches[i % N_SLOTS] for i in range(e2e_steps))):
-                n_p += 1
-            torch.cuda.synchronize()
-            p_dt = time.perf_counter() - t0
-            p_val = n_p * B_TRAIN * T / p_dt
-            e2e["sequential_value"] = e2e["value"]
-            e2e["pipelined_value"] = p_val
-            if n_p == e2e_steps and loss_val == loss_val and p_val > e2e["value"]:      # finite loss, all steps ran
-                e2e["value"] = p_val
-                e2e["mode"] = "pipelined (double-buffered H2D on a copy stream)"
-                e2e["api"] = "runner.pipelined_steps(TrainStepRunner, pinned batches): load + step + loss.item() per step"
+            dp_parity.update(dp_parity_check(b2h, synthetic, DataParallelTrainer, TrainStepRunner, dev, rank, world, train_prec,
+                                             args.exchange, not args.no_multicast))
         except Exception as ex:   # noqa: BLE001
-            e2e["pipelined_error"] = str(ex)[:200]
-    runner.finish()
+            dp_parity["error"] = f"{type(ex).__name__}: {ex}"[:300]
+    try:
+        runner.finish()
+        status_ok = True
+    except Exception as ex:   # noqa: BLE001
+        status_ok = False
+        sys.stderr.write(f"[bench] {ex}\n")
 
     line = {"metric": "body2hand_train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / timed_steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if train_prec == "fp32" else "bf16", "data": "synthetic",
+            "repeats": repeats, "timed_steps": timed_steps, "timed_region_ms": ms,
             "config": {"workload": f"train step (fwd+mask+L1+bwd+Adam), batch {B_TRAIN}x{T} frames per GPU, C={C} (BASELINE config 3/4)",
                        "global_batch": B_TRAIN * world, "frames_per_window": T, "conv_channels": C,
                        "parallelism": f"dp{world}", "cuda_graph": graphed,
                        "grad_exchange": (getattr(runner, "exchange", None) if world > 1 else None),
+                       "timing": f"{repeats} x {args.steps} steps timed back to back after {max(args.warmup, chunk)} warm-up steps "
+                                 f"of the same CUDA graph and one untimed {args.steps}-step pass that aligns the ranks",
                        "l2": f"{N_SLOTS} resident batches rotated ({N_SLOTS * (h2d) / 1e6:.0f} MB inputs + "
                              f"{_lib.workspace_bytes(B_TRAIN, T, 24, C, 0, _lib.PRECISIONS[train_prec]) / 1e6:.0f} MB gradient partials) > 126 MB L2"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "final_loss": final_loss}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "final_loss": final_loss,
+            "tc_status": tc_status, "status_ok": status_ok}
+    if world > 1:
+        line["dp_parity"] = dp_parity
+        line["comm_nranks"] = int(runner.peers_seen)
 
     if rank == 0 and world == 1:
         # ---------------- roofline of the dominant kernel (fused fwd+loss+bwd), timed alone ----------------
@@ -317,7 +374,7 @@ def main():
 
         def train_kernel_only(slot):
             _lib.check(lib.b2h_train_forward_backward(
-                _lib.ptr(runner.x[slot]), _lib.DT_F32, _lib.ptr(runner.target[slot]), None, _lib.ptr(runner.lengths[slot]),
+                _lib.ptr(runner.x[slot]), runner._x_dt(), _lib.ptr(runner.target[slot]), None, _lib.ptr(runner.lengths[slot]),
                 _lib.ptr(model._flat), _lib.ptr(runner.packed), None, None, None, B_TRAIN, T, n_in, Cc, pe, _lib.LOSS_L1,
                 _lib.PRECISIONS[model.precision], None, _lib.ptr(runner.ws), runner.ws.numel(), _lib.stream_ptr(dev)))
 
@@ -339,7 +396,7 @@ def main():
         torch.cuda.synchronize()
         k_only_ms = ev0.elapsed_time(ev1) / reps            # forward+loss+backward kernel without the fused tail
         fused = launches_per_step == 1                      # bf16 mode: the whole step IS one kernel launch
-        k_ms = (ms / args.steps) if fused else k_only_ms
+        k_ms = (ms / timed_steps) if fused else k_only_ms
         tfl = TRAIN_FLOP_PER_WINDOW * B_TRAIN / (k_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -351,6 +408,68 @@ def main():
                             "peak_source": pk["source"] + ", bf16 dense sustained",
                             "note": "bf16 mode: one cooperative launch per step (fwd+loss+bwd, grid barrier, reduction, Adam), timed over the graph-replayed steps (inter-kernel gaps included); kernel_ms_fwd_bwd_only = the same kernel without its reduction/Adam tail; per-launch device times are in profiles/"}
 
+        def time_train(prec, Bx, Tx, Cx=C, slots=8, reps=6):
+            """graph-replayed train steps of another precision / shape (same API, same step definition)"""
+            torch.manual_seed(0)
+            mm = b2h.ConvModel(Cx, "ReLU", False, precision=prec).to(dev)
+            oo = b2h.FusedAdam(mm.parameters(), lr=LR)
+            rr = TrainStepRunner(mm, oo, Bx, Tx, "L1", n_slots=slots)
+            for s_ in range(slots):
+                rr.load(synthetic.model_batch(Bx, Tx, seed=500 + s_), slot=s_, non_blocking=False)
+            rr.capture(slots)
+            rr.replay(); rr.replay()
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(reps):
+                rr.replay()
+            ev1.record()
+            torch.cuda.synchronize()
+            rr.finish()
+            t_ms = ev0.elapsed_time(ev1) / (reps * slots)
+            sm = 24 * Cx + 2 * Cx * Cx + 42 * Cx
+            flop = 2 * (5 * Tx - 6) * (3 * sm - 24 * Cx) * Bx
+            return {"value": Bx * Tx / (t_ms * 1e-3), "unit": "frames/s", "ms_per_step": t_ms, "dtype": "f32" if prec == "fp32" else "bf16",
+                    "workload": f"train step, batch {Bx}x{Tx}, C={Cx}, CUDA graph", "final_loss": float(rr.loss[0].item()),
+                    "kernel": {1: "ffma", 2: "tcgen05 tile", 5: "tcgen05 wide"}.get(int(lib.b2h_kernel_choice(Tx, 24, Cx, 0, _lib.PRECISIONS[prec], 1)), "?"),
+                    "roofline": {"bound": "tensor", "achieved": flop / (t_ms * 1e-3) / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
+                                 "frac": flop / (t_ms * 1e-3) / 1e12 / pk["tflops"]}}
+
+        def time_fwd(prec, Bx, Tx, Cx=C, slots=8, reps=6, x_dtype=None):
+            torch.manual_seed(0)
+            mm = b2h.ConvModel(Cx, "ReLU", False, precision=prec).to(dev)
+            xd = x_dtype or (torch.bfloat16 if prec == "bf16" else torch.float32)
+            ff = ForwardRunner(mm, Bx, Tx, n_slots=slots, x_dtype=xd)
+            for s_ in range(slots):
+                ff.x[s_].copy_(synthetic.model_batch(Bx, Tx, seed=600 + s_)["input_kp"])
+            ff.capture(slots)
+            ff.graph.replay(); ff.graph.replay()
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(reps):
+                ff.graph.replay()
+            ev1.record()
+            torch.cuda.synchronize()
+            t_ms = ev0.elapsed_time(ev1) / (reps * slots)
+            sm = 24 * Cx + 2 * Cx * Cx + 42 * Cx
+            flop = 2 * (5 * Tx - 6) * sm * Bx
+            return {"value": Bx * Tx / (t_ms * 1e-3), "unit": "frames/s", "ms_per_batch": t_ms, "dtype": "f32" if prec == "fp32" else "bf16",
+                    "workload": f"forward, batch {Bx}x{Tx}, C={Cx}, CUDA graph",
+                    "roofline": {"bound": "tensor", "achieved": flop / (t_ms * 1e-3) / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
+                                 "frac": flop / (t_ms * 1e-3) / 1e12 / pk["tflops"]}}
+
+        if not args.skip_extras:
+            # ---------------- the same configs in fp32 mode (the reference's own precision, 1e-4 parity), the reference's
+            # default shape (run.py:28,43: batch 128, 200-frame crops) and BASELINE config 1 (one 64-frame window) ----------------
+            for key, fn in (("train_fp32", lambda: time_train("fp32", B_TRAIN, T)),
+                            ("fwd_fp32", lambda: time_fwd("fp32", B_FWD, T)),
+                            ("train_ref_default_shape", lambda: time_train(train_prec, 128, 200)),
+                            ("train_ref_default_shape_fp32", lambda: time_train("fp32", 128, 200)),
+                            ("fwd_config1_latency", lambda: time_fwd(fwd_prec, 1, T, slots=4, reps=50)),
+                            ("fwd_config1_latency_fp32", lambda: time_fwd("fp32", 1, T, slots=4, reps=50))):
+                try:
+                    line[key] = fn()
+                except Exception as ex:   # noqa: BLE001
+                    line[key] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
         if not args.skip_extras:
             # ---------------- config 2: forward, batch 512 x 64, bf16 tensor-core path ----------------
             torch.manual_seed(0)

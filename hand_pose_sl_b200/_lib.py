@@ -28,6 +28,7 @@ _SIGNATURES = {
     "b2h_param_count": (c_int64, [c_int, c_int, c_int]),
     "b2h_param_offset": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "b2h_packed_bytes": (c_int64, [c_int, c_int, c_int]),
+    "b2h_gp_layout_check": (c_int64, [c_int, c_int, c_int]),
     "b2h_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "b2h_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "b2h_forward_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
@@ -50,21 +51,22 @@ _SIGNATURES = {
     "b2h_pose_l1": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                             c_void_p, c_void_p]),
     "b2h_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double,
-                              c_int64, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+                              c_int64, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2h_train_step": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
-                               c_double, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
+                               c_double, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b2h_train_forward_backward_dp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                               c_void_p, c_int64, c_void_p]),
     "b2h_adam_step_dp": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_double, c_double, c_double,
-                                 c_double, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+                                 c_double, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
     "b2h_train_step_dp": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_double, c_double,
-                                  c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p, c_int64,
-                                  c_void_p]),
+                                  c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
+                                  c_void_p, c_int64, c_void_p]),
     "b2h_dp_exchange_floats": (c_int64, [c_int, c_int, c_int, c_int]),
     "b2h_dp_status": (c_int, []),
+    "b2h_pos_emb_concat": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b2h_format_prediction": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "b2h_tc_probe": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b2h_tc_status": (c_int, []),

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
 #include <cmath>
 
 #include "b2h_common.cuh"
@@ -80,6 +81,28 @@ extern "C" int64_t b2h_param_offset(int n_in, int C, int pos_emb, int layer, int
   Geo g = make_geo(n_in, C, pos_emb);
   return is_bias ? g.b_off[layer - 1] : g.w_off[layer - 1];
 }
+/* Host-side self-check of the gradient-partial slot layout (no GPU): every flat parameter index maps to a distinct
+ * slot and back, every other slot decodes as padding.  Returns the number of violations (0 = consistent). */
+extern "C" int64_t b2h_gp_layout_check(int n_in, int C, int pos_emb) {
+  if (!geo_ok(n_in, C, pos_emb, "b2h_gp_layout_check")) return B2H_ESHAPE;
+  Geo g = make_geo(n_in, C, pos_emb);
+  const int nj = gp_total(g);
+  int64_t bad = (nj & 3) ? 1 : 0;
+  for (int l = 0; l < 4; ++l) bad += (gp_layer_off(g, l) & 3) ? 1 : 0;
+  int64_t real = 0;
+  for (int j = 0; j < nj; ++j) {
+    const int i = flat_index_of_gp(g, j);
+    if (i < 0) continue;
+    ++real;
+    if (i >= g.P || gp_index_of_flat(g, i) != j) ++bad;
+  }
+  if (real != g.P) ++bad;
+  for (int i = 0; i < g.P; ++i) {
+    const int j = gp_index_of_flat(g, i);
+    if (j < 0 || j >= nj || flat_index_of_gp(g, j) != i) ++bad;
+  }
+  return bad;
+}
 extern "C" int64_t b2h_packed_bytes(int n_in, int C, int pos_emb) {
   if (!geo_ok(n_in, C, pos_emb, "b2h_packed_bytes")) return B2H_ESHAPE;
   return make_geo(n_in, C, pos_emb).packed_bytes;
@@ -105,10 +128,10 @@ extern "C" int b2h_kernel_choice(int T, int n_in, int C, int pos_emb, int precis
 }
 extern "C" int64_t b2h_workspace_bytes(int B, int T, int n_in, int C, int pos_emb, int precision) {
   if (!geo_ok(n_in, C, pos_emb, "b2h_workspace_bytes")) return B2H_ESHAPE;
-  if (B < 1 || T < 1) return 256;
+  if (B < 1 || T < 1) return B2H_WS_HEADER + 256;
   Geo g = make_geo(n_in, C, pos_emb);
   const int np = train_nparts(g, B, T, precision);
-  return ((int64_t)np * train_part_stride(g, T, precision) + np) * 4 + 256;
+  return B2H_WS_HEADER + ((int64_t)np * train_part_stride(g, T, precision) + np) * 4 + 256;
 }
 
 extern "C" int b2h_pack_weights(const float* params, void* packed, int n_in, int C, int pos_emb, void* stream) {
@@ -181,9 +204,11 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
   }
   nparts = train_nparts(g, B, T, precision);
   const int64_t stride = train_part_stride(g, T, precision);
-  const int64_t need = ((int64_t)nparts * stride + nparts) * 4 + 64;   // + grid-barrier words of the fused kernel
+  const int64_t need = B2H_WS_HEADER + ((int64_t)nparts * stride + nparts) * 4;
   if (workspace_bytes < need) { set_error("%s: workspace %lld B < %lld B", who, (long long)workspace_bytes, (long long)need); return B2H_EWORKSPACE; }
-  partials = reinterpret_cast<float*>(workspace);
+  if (reinterpret_cast<uintptr_t>(workspace) & 15) { set_error("%s: workspace must be 16-byte aligned", who); return B2H_EALIGN; }
+  // [header: launch sequence + per-CTA arrival flags of the fused kernel, FIXED offset][gradient partials][loss partials]
+  partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + B2H_WS_HEADER);
   loss_partials = partials + (size_t)nparts * stride;
   // fp32 mode: FFMA kernel.  bf16 mode: tcgen05 tile kernel (T <= 256, C <= 32); other bf16 shapes fall
   // back to the FFMA kernel -- still CUDA, still fp32 master weights.
@@ -194,8 +219,9 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
   a.step_dev = step_dev;
   a.epoch_dev = epoch_dev;
   if (fuse && use_tc_train(g, T, precision)) {
+    if (nparts > B2H_WS_MAX_CTA) { set_error("%s: %d CTAs exceed the %d arrival flags of the workspace header", who, nparts, B2H_WS_MAX_CTA); return B2H_ESHAPE; }
     fuse->enabled = 1;
-    fuse->sync = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(workspace) + (((int64_t)nparts * stride + nparts) * 4 + 15) / 16 * 16);
+    fuse->hdr = reinterpret_cast<unsigned*>(workspace);
     a.fuse = *fuse;
   }
   if (use_tc_train(g, T, precision)) return launch_tc_tile_train(a, stream);
@@ -234,8 +260,8 @@ extern "C" int b2h_train_forward_backward_dp(const void* x, int x_dtype, const f
 
 extern "C" int b2h_adam_step_dp(float* params, const void* peer_bufs_dev, int rank, int world, float* exp_avg, float* exp_avg_sq,
                                 int64_t n, double lr, double beta1, double beta2, double eps, const int64_t* step_dev,
-                                const int64_t* epoch_dev, float grad_scale, void* packed, int n_in, int C, int pos_emb,
-                                void* stream) {
+                                const int64_t* epoch_dev, const double* lr_dev, float grad_scale, void* packed, int n_in, int C,
+                                int pos_emb, void* stream) {
   if (!params || !peer_bufs_dev || !exp_avg || !exp_avg_sq || !step_dev || !epoch_dev) { set_error("b2h_adam_step_dp: null pointer"); return B2H_EINVAL; }
   if (world < 1 || world > 32 || rank < 0 || rank >= world) { set_error("b2h_adam_step_dp: bad rank/world"); return B2H_EINVAL; }
   if (!geo_ok(n_in, C, pos_emb, "b2h_adam_step_dp")) return B2H_ESHAPE;
@@ -243,7 +269,7 @@ extern "C" int b2h_adam_step_dp(float* params, const void* peer_bufs_dev, int ra
   if (g.P != n) { set_error("b2h_adam_step_dp: n=%lld does not match geometry (%d)", (long long)n, g.P); return B2H_ESHAPE; }
   return launch_adam_dp(params, reinterpret_cast<const float* const*>(peer_bufs_dev), rank, world, exp_avg, exp_avg_sq, n, lr, beta1,
                         beta2, eps, reinterpret_cast<const long long*>(step_dev), reinterpret_cast<const long long*>(epoch_dev),
-                        grad_scale, packed, g, (cudaStream_t)stream);
+                        lr_dev, grad_scale, packed, g, (cudaStream_t)stream);
 }
 
 extern "C" int64_t b2h_dp_exchange_floats(int n_in, int C, int pos_emb, int world) {
@@ -272,7 +298,7 @@ extern "C" int b2h_conv_backward(const void* x, int x_dtype, const float* d_y, c
 extern "C" int b2h_train_step(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,
                               float* params, void* packed, float* exp_avg, float* exp_avg_sq, float* loss_out, int B,
                               int T, int n_in, int C, int pos_emb, int loss_kind, int precision, double lr, double beta1,
-                              double beta2, double eps, int64_t step, int64_t* step_dev, void* workspace,
+                              double beta2, double eps, int64_t step, int64_t* step_dev, const double* lr_dev, void* workspace,
                               int64_t workspace_bytes, void* stream) {
   if (!exp_avg || !exp_avg_sq || !loss_out) { set_error("b2h_train_step: null pointer"); return B2H_EINVAL; }
   if (step < 1 && !step_dev) { set_error("b2h_train_step: step must be >= 1"); return B2H_EINVAL; }
@@ -281,6 +307,7 @@ extern "C" int b2h_train_step(const void* x, int x_dtype, const float* target, c
   FuseAdam fuse{};
   fuse.params = params; fuse.m = exp_avg; fuse.v = exp_avg_sq; fuse.packed = reinterpret_cast<char*>(packed);
   fuse.lr = lr; fuse.beta1 = beta1; fuse.beta2 = beta2; fuse.eps = (float)eps; fuse.grad_scale = 1.0f;
+  fuse.lr_dev = lr_dev;
   fuse.step_dev = reinterpret_cast<const long long*>(step_dev); fuse.loss_out = loss_out; fuse.world = 1;
   int rc = train_common(x, x_dtype, target, conf, nullptr, lengths, params, packed, nullptr, B, T, n_in, C, pos_emb,
                         loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
@@ -289,16 +316,16 @@ extern "C" int b2h_train_step(const void* x, int x_dtype, const float* target, c
   if (rc) return rc;
   if (step_dev && use_tc_train(g, T, precision)) return B2H_OK;
   return launch_adam(params, partials, nparts, use_tc_train(g, T, precision) ? 1 : 0, exp_avg, exp_avg_sq, g.P, lr, beta1, beta2, eps, step < 1 ? 1 : step,
-                     reinterpret_cast<const long long*>(step_dev), 1.0f, packed, g,
+                     reinterpret_cast<const long long*>(step_dev), lr_dev, 1.0f, packed, g,
                      loss_partials, loss_out, (cudaStream_t)stream);
 }
 
 extern "C" int b2h_train_step_dp(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,
                                  float* params, void* packed, float* exp_avg, float* exp_avg_sq, float* loss_out, int B, int T,
                                  int n_in, int C, int pos_emb, int loss_kind, int precision, double lr, double beta1,
-                                 double beta2, double eps, int64_t* step_dev, int64_t* epoch_dev, float* sym_grads,
-                                 const void* peer_bufs_dev, int rank, int world, float grad_scale, void* workspace,
-                                 int64_t workspace_bytes, void* stream) {
+                                 double beta2, double eps, int64_t* step_dev, int64_t* epoch_dev, const double* lr_dev,
+                                 float* sym_grads, const void* peer_bufs_dev, void* multicast_buf, int rank, int world,
+                                 float grad_scale, void* workspace, int64_t workspace_bytes, void* stream) {
   if (!exp_avg || !exp_avg_sq || !loss_out || !step_dev || !epoch_dev || !sym_grads || !peer_bufs_dev) {
     set_error("b2h_train_step_dp: null pointer");
     return B2H_EINVAL;
@@ -308,8 +335,10 @@ extern "C" int b2h_train_step_dp(const void* x, int x_dtype, const float* target
   FuseAdam fuse{};
   fuse.params = params; fuse.m = exp_avg; fuse.v = exp_avg_sq; fuse.packed = reinterpret_cast<char*>(packed);
   fuse.lr = lr; fuse.beta1 = beta1; fuse.beta2 = beta2; fuse.eps = (float)eps; fuse.grad_scale = grad_scale;
+  fuse.lr_dev = lr_dev;
   fuse.step_dev = reinterpret_cast<const long long*>(step_dev); fuse.loss_out = loss_out;
   fuse.peer_bufs = reinterpret_cast<const float* const*>(peer_bufs_dev); fuse.sym_grads = sym_grads;
+  fuse.mc_buf = reinterpret_cast<unsigned long long*>(multicast_buf);
   fuse.epoch_dev = reinterpret_cast<const long long*>(epoch_dev); fuse.rank = rank; fuse.world = world;
   int rc = train_common(x, x_dtype, target, conf, nullptr, lengths, params, packed, nullptr, B, T, n_in, C, pos_emb,
                         loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
@@ -322,12 +351,12 @@ extern "C" int b2h_train_step_dp(const void* x, int x_dtype, const float* target
   if (rc) return rc;
   return launch_adam_dp(params, reinterpret_cast<const float* const*>(peer_bufs_dev), rank, world, exp_avg, exp_avg_sq, g.P, lr,
                         beta1, beta2, eps, reinterpret_cast<const long long*>(step_dev),
-                        reinterpret_cast<const long long*>(epoch_dev), grad_scale, packed, g, (cudaStream_t)stream);
+                        reinterpret_cast<const long long*>(epoch_dev), lr_dev, grad_scale, packed, g, (cudaStream_t)stream);
 }
 
 extern "C" int b2h_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
                              double beta1, double beta2, double eps, int64_t step, const int64_t* step_dev,
-                             float grad_scale, void* packed, int n_in, int C, int pos_emb, void* stream) {
+                             const double* lr_dev, float grad_scale, void* packed, int n_in, int C, int pos_emb, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq) { set_error("b2h_adam_step: null pointer"); return B2H_EINVAL; }
   if ((step < 1 && !step_dev) || n < 0) { set_error("b2h_adam_step: bad step/n"); return B2H_EINVAL; }
   Geo g{};
@@ -338,7 +367,7 @@ extern "C" int b2h_adam_step(float* params, const float* grads, float* exp_avg, 
   }
   if (n == 0) return B2H_OK;
   return launch_adam(params, grads, 1, 0, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step < 1 ? 1 : step,
-                     reinterpret_cast<const long long*>(step_dev), grad_scale, packed, g, nullptr, nullptr, (cudaStream_t)stream);
+                     reinterpret_cast<const long long*>(step_dev), lr_dev, grad_scale, packed, g, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int b2h_mask_output(float* y, const int32_t* lengths, int B, int T, int row_elems, void* stream) {
@@ -362,6 +391,16 @@ extern "C" int b2h_format_prediction(const float* pred, float* out, int64_t rows
   return launch_format_prediction(pred, out, rows, mode, (cudaStream_t)stream);
 }
 
+extern "C" int b2h_pos_emb_concat(const float* inp, float* out, int B, int channels, int T, int max_len, void* stream) {
+  if (!inp || !out) { set_error("b2h_pos_emb_concat: null pointer"); return B2H_EINVAL; }
+  if (B < 0 || channels < 1 || T < 1 || max_len < 1) { set_error("b2h_pos_emb_concat: bad shape"); return B2H_ESHAPE; }
+  if (T != max_len) {   // torch.cat of (B,1,max_len) with (B,C,T) fails in the reference (HandPoseModels.py:82)
+    set_error("b2h_pos_emb_concat: Sizes of tensors must match except in dimension 1 (T=%d, max_len=%d)", T, max_len);
+    return B2H_ESHAPE;
+  }
+  return launch_pos_emb_concat(inp, out, B, channels, T, max_len, (cudaStream_t)stream);
+}
+
 extern "C" int b2h_tc_probe(const void* a_bf16, const void* b_bf16, float* out, int n, int ksteps, int shift, int variant,
                             void* stream) {
   if (!a_bf16 || !b_bf16 || !out) { set_error("b2h_tc_probe: null pointer"); return B2H_EINVAL; }
@@ -377,13 +416,41 @@ extern "C" void b2h_debug_timing(void* dev_i64x128) { set_debug_timing(reinterpr
 
 extern "C" int b2h_tc_status(void) { return tc_status_and_clear(); }
 
+namespace {
+constexpr int kMaxDev = 64;
+std::mutex g_cache_mu;
+int g_sms[kMaxDev] = {0};
+struct SmemAttr { const void* fn; size_t bytes[kMaxDev]; };
+SmemAttr g_attr[32] = {};
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+  return dev < 0 ? 0 : dev;
+}
+}  // namespace
+
 int b2h::num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  if (dev < kMaxDev && g_sms[dev]) return g_sms[dev];
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  if (dev < kMaxDev) g_sms[dev] = n;
   return n;
+}
+
+int b2h::ensure_dyn_smem(const void* fn, size_t bytes) {
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  SmemAttr* slot = nullptr;
+  for (auto& a : g_attr) {
+    if (a.fn == fn) { slot = &a; break; }
+    if (!a.fn) { a.fn = fn; slot = &a; break; }
+  }
+  if (slot && dev < kMaxDev && slot->bytes[dev] >= bytes) return B2H_OK;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaFuncSetAttribute(%zu B): %s", bytes, cudaGetErrorString(e)); return B2H_ECUDA; }
+  if (slot && dev < kMaxDev) slot->bytes[dev] = bytes;
+  return B2H_OK;
 }

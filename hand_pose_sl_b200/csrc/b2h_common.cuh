@@ -68,8 +68,11 @@ __host__ __device__ inline int64_t umma_b_offset(int k, int kk, int n, int KP, i
   return q * ((int64_t)N * 32) + (int64_t)chunk * (N * 16) + (int64_t)n * 16 + within * 2;
 }
 
-// Gradient-partial layout written by the tensor-core train kernel (coalesced 128-B rows):
-//   per layer l: W part [k][co][kp_l] then bias part [cout_l]
+// Gradient-partial layout written by the tensor-core train kernel.  The TMEM read-out has lane = output channel
+// and 32 consecutive columns = input channels, so the W part is stored [k][ci/4][co][4 ci]: for a fixed (k, ci/4)
+// the lanes of a warp store consecutive float4s (coalesced; the [k][co][ci] order of round 1 made every lane of a
+// store instruction hit its own 128-B line: ~6k cycles of read-out per CTA).
+//   per layer l: W part [k][kp_l/4][cout_l][4] then bias part [cout_l] (padded to a multiple of 4)
 __host__ __device__ inline int gp_layer_size(const Geo& g, int l) { return B2H_KW * g.cout[l] * g.kp[l] + round_up(g.cout[l], 4); }
 __host__ __device__ inline int gp_layer_off(const Geo& g, int l) {
   int o = 0;
@@ -89,11 +92,12 @@ __host__ __device__ inline int gp_index_of_flat(const Geo& g, int i) {
   const int co = rel / (cin * B2H_KW);
   const int rem = rel - co * cin * B2H_KW;
   const int ci = rem / B2H_KW, k = rem - ci * B2H_KW;
-  return base + (k * g.cout[l] + co) * g.kp[l] + ci;
+  return base + ((k * (g.kp[l] >> 2) + (ci >> 2)) * g.cout[l] + co) * 4 + (ci & 3);
 }
 
-// GP index -> flat parameter index (-1 for the padding slots of the GP layout)
-__host__ __device__ inline int flat_index_of_gp(const Geo& g, int j) {
+// GP index -> (layer, tap, co, ci); is_bias: co = bias index, k = ci = 0.  Returns false for the padding slots.
+struct GpSlot { int l, k, co, ci; bool is_bias; };
+__host__ __device__ inline bool gp_decode(const Geo& g, int j, GpSlot& s) {
   int l = 0, base = 0;
   for (int q = 0; q < 4; ++q) {
     const int sz = gp_layer_size(g, q);
@@ -102,11 +106,25 @@ __host__ __device__ inline int flat_index_of_gp(const Geo& g, int j) {
   }
   const int rel = j - base;
   const int wsz = B2H_KW * g.cout[l] * g.kp[l];
-  if (rel >= wsz) { const int b = rel - wsz; return b < g.cout[l] ? g.b_off[l] + b : -1; }
-  const int k = rel / (g.cout[l] * g.kp[l]);
-  const int r2 = rel - k * g.cout[l] * g.kp[l];
-  const int co = r2 / g.kp[l], ci = r2 - co * g.kp[l];
-  return ci < g.cin[l] ? g.w_off[l] + (co * g.cin[l] + ci) * B2H_KW + k : -1;
+  s.l = l;
+  if (rel >= wsz) { s.is_bias = true; s.k = 0; s.ci = 0; s.co = rel - wsz; return s.co < g.cout[l]; }
+  s.is_bias = false;
+  const int e = rel & 3;
+  int r = rel >> 2;
+  const int q4 = g.kp[l] >> 2;
+  s.co = r % g.cout[l]; r /= g.cout[l];
+  const int qq = r % q4;
+  s.k = r / q4;
+  s.ci = 4 * qq + e;
+  return s.ci < g.cin[l];
+}
+__host__ __device__ inline int gp_flat_of_slot(const Geo& g, const GpSlot& s) {
+  return s.is_bias ? g.b_off[s.l] + s.co : g.w_off[s.l] + (s.co * g.cin[s.l] + s.ci) * B2H_KW + s.k;
+}
+// GP index -> flat parameter index (-1 for the padding slots of the GP layout)
+__host__ __device__ inline int flat_index_of_gp(const Geo& g, int j) {
+  GpSlot s;
+  return gp_decode(g, j, s) ? gp_flat_of_slot(g, s) : -1;
 }
 
 // Scatter one fp32 parameter (flat index i) into the packed operand layouts.
@@ -135,6 +153,25 @@ __device__ __forceinline__ void scatter_packed(const Geo& g, char* packed, int i
 }
 
 
+// Same scatter from a decoded gradient-partial slot (the fused train kernel decodes its slots before the grid barrier).
+__device__ __forceinline__ void scatter_packed_slot(const Geo& g, char* packed, const GpSlot& s, float v) {
+  const int l = s.l;
+  if (s.is_bias) {
+    if (s.co < 64) reinterpret_cast<float*>(packed + g.bias_off)[l * 64 + s.co] = v;
+    return;
+  }
+  const int cin = g.cin[l], cout = g.cout[l], co = s.co, ci = s.ci, k = s.k;
+  reinterpret_cast<float*>(packed + g.wf_off[l])[(k * cin + ci) * cout + co] = v;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(packed + g.tf_off[l] + umma_b_offset(k, ci, co, g.kp[l], g.np_[l])) = h;
+  if (l > 0) {
+    reinterpret_cast<float*>(packed + g.wd_off[l])[((B2H_KW - 1 - k) * cout + co) * cin + ci] = v;
+    *reinterpret_cast<__nv_bfloat16*>(packed + g.td_off[l] +
+                                      umma_b_offset(B2H_KW - 1 - k, co, ci, round_up(cout, 16), round_up(cin, 16))) = h;
+  }
+}
+
+
 // beta^t for an integer step count by binary exponentiation (~2*log2(t) DMULs instead of a double-precision pow())
 __host__ __device__ inline double ipow(double b, long long t) {
   double r = 1.0;
@@ -146,19 +183,29 @@ __host__ __device__ inline double ipow(double b, long long t) {
   return r;
 }
 
+// Workspace header of the fused train kernel (first B2H_WS_HEADER bytes of the caller's workspace, zeroed once when the
+// workspace is allocated and owned by the kernels afterwards; FIXED offset, so runners of different (B, T) that share
+// one workspace can never find gradient partials where they expect barrier words):
+//   u32 [0]        launch sequence number (read by every CTA at kernel start, advanced by CTA 0 after the grid barrier)
+//   u32 [4 + c]    arrival flag of CTA c (= sequence number of the launch it last arrived in)
+#define B2H_WS_HEADER 1024
+#define B2H_WS_MAX_CTA 192
+
 // Optional tail of the tensor-core train kernel: cross-CTA gradient reduction, (data-parallel) gradient exchange
-// over peer memory and Adam, all inside the SAME cooperative launch (grid barriers through `sync`).
+// over peer memory and Adam, all inside the SAME cooperative launch (grid barrier through the workspace header).
 struct FuseAdam {
   int enabled;
   float* params; float* m; float* v; char* packed;
   double lr, beta1, beta2;
+  const double* lr_dev;              // nullable: learning rate read from device memory (a captured graph follows lr changes)
   float eps, grad_scale;
   const long long* step_dev;
   float* loss_out;
-  unsigned* sync;                    // [2] zero-initialised words: arrival counter, generation
+  unsigned* hdr;                     // workspace header (B2H_WS_HEADER bytes)
   // data parallel (world > 1)
-  const float* const* peer_bufs;     // device array [world] of peer exchange buffers ([2][P] fp32 + [world] int64 flags)
+  const float* const* peer_bufs;     // device array [world] of peer exchange buffers
   float* sym_grads;                  // this rank's exchange buffer
+  unsigned long long* mc_buf;        // nullable: multicast (NVLS) address of the exchange buffers: one multimem.st reaches every rank
   const long long* epoch_dev;
   int rank, world;
 };
@@ -213,19 +260,23 @@ int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream);
 void set_debug_timing(long long* p);
 int launch_tc_bench(long long* out, int M, int N, int reps, int nacc, int mn_major, cudaStream_t stream);
 int launch_format_prediction(const float* pred, float* out, int64_t rows, int mode, cudaStream_t stream);
+int launch_pos_emb_concat(const float* inp, float* out, int B, int Cc, int T, int max_len, cudaStream_t stream);
 int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t stream);
 int launch_reduce(const float* partials, int nparts, int gp_layout, const Geo& g, float* grads, const float* loss_partials,
                   float* loss_out, cudaStream_t stream, const long long* epoch_dev = nullptr);
 int launch_adam_dp(float* params, const float* const* peer_bufs, int rank, int world, float* m, float* v, int64_t n, double lr,
-                   double beta1, double beta2, double eps, const long long* step_dev, const long long* epoch_dev, float grad_scale,
-                   void* packed, const Geo& g, cudaStream_t stream);
+                   double beta1, double beta2, double eps, const long long* step_dev, const long long* epoch_dev, const double* lr_dev,
+                   float grad_scale, void* packed, const Geo& g, cudaStream_t stream);
 int dp_status_and_clear();
 int launch_adam(float* params, const float* grads, int nparts, int gp_layout, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
-                double eps, int64_t step, const long long* step_dev, float grad_scale, void* packed, const Geo& g,
+                double eps, int64_t step, const long long* step_dev, const double* lr_dev, float grad_scale, void* packed, const Geo& g,
                 const float* loss_partials, float* loss_out, cudaStream_t stream);
 int launch_mask_output(float* y, const int32_t* lengths, int B, int T, int row, cudaStream_t stream);
 int launch_pose_l1(const float* pred, const float* target, const float* scores, const int32_t* lengths, int B, int T, int row,
                    int loss_kind, float* loss_out, float* d_pred, float* row_scratch, cudaStream_t stream);
-int num_sms();
+int num_sms();                                        // SM count of the CURRENT device (cached per device)
+// cudaFuncAttributeMaxDynamicSharedMemorySize for `fn` on the CURRENT device, raised on demand; the cache is keyed by
+// (function, device) so that one process can drive several GPUs (inference replicas).  Returns B2H_OK / B2H_ECUDA.
+int ensure_dyn_smem(const void* fn, size_t bytes);
 
 }  // namespace b2h

@@ -320,13 +320,8 @@ int launch_fp32(Fp32Args& p, bool train, cudaStream_t stream, int grid_override)
     return B2H_ESHAPE;
   }
   // opt in to > 48 KB of dynamic shared memory (dynamic + static must stay <= 227 KB)
-  static size_t attr_bytes[2] = {0, 0};
-  if (smem > attr_bytes[train ? 1 : 0]) {
-    cudaError_t e = train ? cudaFuncSetAttribute(conv_fp32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                          : cudaFuncSetAttribute(conv_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e)); return B2H_ECUDA; }
-    attr_bytes[train ? 1 : 0] = smem;
-  }
+  if (int rc = ensure_dyn_smem(train ? reinterpret_cast<const void*>(conv_fp32_kernel<true>) : reinterpret_cast<const void*>(conv_fp32_kernel<false>), smem))
+    return rc;
   int grid;
   if (train) {
     grid = grid_override > 0 ? grid_override : fp32_train_grid(p.geo, p.B, p.T);

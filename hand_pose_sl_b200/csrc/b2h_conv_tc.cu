@@ -309,12 +309,7 @@ int launch_tc_fwd(TcFwdArgs& p, cudaStream_t stream) {
     set_error("bf16 forward: T=%d C=%d needs %zu B shared memory", p.T, p.geo.C, smem);
     return B2H_ESHAPE;
   }
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e)); return B2H_ECUDA; }
-    attr_bytes = smem;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_fwd_kernel), smem)) return rc;
   const int grid = (p.B + p.G - 1) / p.G;
   conv_tc_fwd_kernel<<<grid, kTcThreads, smem, stream>>>(p);
   count_launch();
@@ -330,11 +325,7 @@ int launch_tc_probe(const void* a, const void* b, float* out, int n, int ksteps,
   }
   const int K = 16 * ksteps;
   const size_t bytes = (mode == 1) ? (size_t)16 * K * 16 + (size_t)(n / 8) * (K + 8) * 16 : (size_t)(K / 8) * 136 * 16 + (size_t)(K / 8) * n * 16;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(tc_probe_kernel), 200 * 1024)) return rc;
   tc_probe_kernel<<<1, 128, bytes + 128, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<const __nv_bfloat16*>(b), out, n,
                                                    ksteps, shift, variant, mode);
   count_launch();
@@ -344,7 +335,10 @@ int launch_tc_probe(const void* a, const void* b, float* out, int n, int ksteps,
 int tc_status_and_clear() {
   int v = 0, z = 0;
   cudaMemcpyFromSymbol(&v, g_tc_status, sizeof(int));
-  if (v) cudaMemcpyToSymbol(g_tc_status, &z, sizeof(int));
+  if (v) {
+    cudaMemcpyToSymbol(g_tc_status, &z, sizeof(int));
+    cudaMemcpyToSymbol(g_dp_abort, &z, sizeof(int));
+  }
   return v;
 }
 
@@ -458,8 +452,7 @@ __global__ void __launch_bounds__(32) tma_bench_kernel(long long* out, int copy_
 int launch_tc_bench(long long* out, int M, int N, int reps, int nacc, int mn_major, cudaStream_t stream) {
   if (M == 1) {   // TMA bulk-copy throughput: N = bytes per copy, reps = rounds, nacc = ring depth, mn_major = CTAs
     if (N < 16 || N > 8192 || (8192 % N) || nacc < 1 || nacc > 16 || reps < 1 || mn_major < 1) { set_error("b2h_tc_bench(tma): bad arguments"); return B2H_EINVAL; }
-    static bool attr2 = false;
-    if (!attr2) { cudaFuncSetAttribute(tma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); attr2 = true; }
+    if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(tma_bench_kernel), 128 * 1024)) return rc;
     tma_bench_kernel<<<mn_major, 32, 128 * 1024, stream>>>(out, N, reps, nacc);
     count_launch();
     return check_launch("tma_bench_kernel");
@@ -468,8 +461,7 @@ int launch_tc_bench(long long* out, int M, int N, int reps, int nacc, int mn_maj
     set_error("b2h_tc_bench: bad arguments");
     return B2H_EINVAL;
   }
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(tc_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(tc_bench_kernel), 64 * 1024)) return rc;
   const int grid = (mn_major >> 8) > 0 ? (mn_major >> 8) : 1;     // bits 8..: CTAs (all SMs busy -> chip-level pacing)
   tc_bench_kernel<<<grid, 128, 64 * 1024, stream>>>(out, M, N, reps, nacc, mn_major & 255, 136);
   count_launch();

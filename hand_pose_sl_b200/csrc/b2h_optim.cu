@@ -73,7 +73,9 @@ struct AdamArgs {
   float* m; float* v;
   float beta1, beta2, one_minus_b1, one_minus_b2, step_size, inv_bc2_sqrt, eps, grad_scale;
   double lr_d, beta1_d, beta2_d;
+  long long step_host;
   const long long* step_dev;
+  const double* lr_dev;            // nullable: learning rate in device memory (captured graphs follow lr changes)
   char* packed; Geo g;
   const float* loss_partials; float* loss_out;
 };
@@ -84,10 +86,11 @@ struct AdamArgs {
 __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
   __shared__ float red[8][32];
   __shared__ float s_step_size, s_inv_bc2_sqrt;
-  if (a.step_dev) {   // bias corrections from the device-side step counter (graph replay)
+  if (a.step_dev || a.lr_dev) {   // bias corrections from the device-side step counter / learning rate (graph replay)
     if (threadIdx.x == 0) {
-      const long long t = *a.step_dev;
-      s_step_size = (float)(a.lr_d / (1.0 - ipow(a.beta1_d, t)));
+      const long long t = a.step_dev ? *a.step_dev : a.step_host;
+      const double lr = a.lr_dev ? *a.lr_dev : a.lr_d;
+      s_step_size = (float)(lr / (1.0 - ipow(a.beta1_d, t)));
       s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - ipow(a.beta2_d, t)));
     }
     __syncthreads();
@@ -143,11 +146,15 @@ __global__ void __launch_bounds__(256) adam_dp_kernel(AdamDpArgs d) {
   const long long epoch = *d.epoch_dev;
   const size_t P = (size_t)a.n;
   const size_t flag_off = 2 * P;                       // in floats; flags are 8-byte aligned (2P is even)
+  __shared__ int s_abort;
   if (threadIdx.x == 0) {
     const long long t = *a.step_dev;
-    s_step_size = (float)(a.lr_d / (1.0 - ipow(a.beta1_d, t)));
+    const double lr = a.lr_dev ? *a.lr_dev : a.lr_d;
+    s_step_size = (float)(lr / (1.0 - ipow(a.beta1_d, t)));
     s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - ipow(a.beta2_d, t)));
+    s_abort = 0;
   }
+  __syncthreads();
   if (blockIdx.x == 0 && threadIdx.x < d.world) {
     __threadfence_system();
     volatile long long* f = reinterpret_cast<volatile long long*>(const_cast<float*>(d.peer_bufs[threadIdx.x]) + flag_off) + d.rank;
@@ -158,11 +165,14 @@ __global__ void __launch_bounds__(256) adam_dp_kernel(AdamDpArgs d) {
     const volatile long long* f = reinterpret_cast<const volatile long long*>(d.peer_bufs[d.rank] + flag_off) + threadIdx.x;
     const long long t0 = clock64();
     while (*f < epoch) {
-      if (clock64() - t0 > 6000000000LL) { atomicExch(&g_dp_status, 1); break; }   // ~3 s: never hang the box
+      if (clock64() - t0 > 6000000000LL) { atomicExch(&g_dp_status, 1); s_abort = 1; break; }   // ~3 s: never hang the box
     }
     __threadfence_system();
   }
   __syncthreads();
+  // Sticky abort: once a peer wait has timed out, no parameter / moment is written (this step and every later one)
+  // until the host has read and cleared the status -- replicas may stall, they never silently diverge.
+  if (s_abort || *reinterpret_cast<volatile int*>(&g_dp_status) != 0) return;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < a.n) {
     const size_t off = (size_t)(epoch & 1) * P + (size_t)i;
@@ -180,8 +190,8 @@ __global__ void __launch_bounds__(256) adam_dp_kernel(AdamDpArgs d) {
 }
 
 int launch_adam_dp(float* params, const float* const* peer_bufs, int rank, int world, float* m, float* v, int64_t n, double lr,
-                   double beta1, double beta2, double eps, const long long* step_dev, const long long* epoch_dev, float grad_scale,
-                   void* packed, const Geo& g, cudaStream_t stream) {
+                   double beta1, double beta2, double eps, const long long* step_dev, const long long* epoch_dev, const double* lr_dev,
+                   float grad_scale, void* packed, const Geo& g, cudaStream_t stream) {
   AdamDpArgs d{};
   AdamArgs& a = d.a;
   a.params = params; a.grads = nullptr; a.nparts = 1; a.gp_layout = 0; a.n = n; a.m = m; a.v = v;
@@ -189,7 +199,7 @@ int launch_adam_dp(float* params, const float* const* peer_bufs, int rank, int w
   a.one_minus_b1 = (float)(1.0 - beta1); a.one_minus_b2 = (float)(1.0 - beta2);
   a.eps = (float)eps; a.grad_scale = grad_scale;
   a.packed = reinterpret_cast<char*>(packed); a.g = g;
-  a.lr_d = lr; a.beta1_d = beta1; a.beta2_d = beta2; a.step_dev = step_dev;
+  a.lr_d = lr; a.beta1_d = beta1; a.beta2_d = beta2; a.step_dev = step_dev; a.lr_dev = lr_dev; a.step_host = 1;
   d.peer_bufs = peer_bufs; d.epoch_dev = epoch_dev; d.rank = rank; d.world = world;
   adam_dp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d);
   count_launch();
@@ -283,6 +293,28 @@ __global__ void format_prediction_kernel(const float* __restrict__ pred, float* 
   }
 }
 
+// LinearPositionalEmbedding.forward  body2hand/src/models/HandPoseModels.py:78-84: out (B, C+1, T) = cat([t / max_len, inp (B, C, T)], dim=1)
+__global__ void pos_emb_concat_kernel(const float* __restrict__ inp, float* __restrict__ out, int B, int Cc, int T, float max_len) {
+  const int64_t n = (int64_t)B * (Cc + 1) * T;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T);
+    const int64_t bc = i / T;
+    const int c = (int)(bc % (Cc + 1));
+    const int64_t b = bc / (Cc + 1);
+    out[i] = c == 0 ? __fdiv_rn((float)t, max_len) : inp[(b * Cc + (c - 1)) * T + t];
+  }
+}
+
+int launch_pos_emb_concat(const float* inp, float* out, int B, int Cc, int T, int max_len, cudaStream_t stream) {
+  const int64_t n = (int64_t)B * (Cc + 1) * T;
+  if (n == 0) return B2H_OK;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pos_emb_concat_kernel<<<(unsigned)blocks, 256, 0, stream>>>(inp, out, B, Cc, T, (float)max_len);
+  count_launch();
+  return check_launch("pos_emb_concat_kernel");
+}
+
 int launch_format_prediction(const float* pred, float* out, int64_t rows, int mode, cudaStream_t stream) {
   if (rows == 0) return B2H_OK;
   int64_t blocks = (rows * 63 + 255) / 256;
@@ -307,8 +339,8 @@ int launch_reduce(const float* partials, int nparts, int gp_layout, const Geo& g
 }
 
 int launch_adam(float* params, const float* grads, int nparts, int gp_layout, float* m, float* v, int64_t n, double lr, double beta1,
-                double beta2, double eps, int64_t step, const long long* step_dev, float grad_scale, void* packed, const Geo& g,
-                const float* loss_partials, float* loss_out, cudaStream_t stream) {
+                double beta2, double eps, int64_t step, const long long* step_dev, const double* lr_dev, float grad_scale, void* packed,
+                const Geo& g, const float* loss_partials, float* loss_out, cudaStream_t stream) {
   AdamArgs a;
   a.params = params; a.grads = grads; a.nparts = nparts; a.gp_layout = gp_layout; a.n = n; a.m = m; a.v = v;
   a.beta1 = (float)beta1; a.beta2 = (float)beta2;
@@ -319,7 +351,7 @@ int launch_adam(float* params, const float* grads, int nparts, int gp_layout, fl
   a.eps = (float)eps; a.grad_scale = grad_scale;
   a.packed = reinterpret_cast<char*>(packed); a.g = g;
   a.loss_partials = loss_partials; a.loss_out = loss_out;
-  a.lr_d = lr; a.beta1_d = beta1; a.beta2_d = beta2; a.step_dev = step_dev;
+  a.lr_d = lr; a.beta1_d = beta1; a.beta2_d = beta2; a.step_dev = step_dev; a.lr_dev = lr_dev; a.step_host = step;
   const int64_t nj = gp_layout ? (int64_t)gp_total(g) : n;
   if (nparts == 1) adam_kernel<<<(unsigned)((nj + 31) / 32), 32, 0, stream>>>(a);
   else adam_kernel<<<(unsigned)((nj + 31) / 32), 256, 0, stream>>>(a);

@@ -48,6 +48,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // Device-side status word: a wait that exceeds its budget records the site and returns so a
 // descriptor / protocol bug ends as a wrong answer + error code, never as a hung GPU.
 __device__ int g_tc_status = 0;
+// Data-parallel exchange: set (with status 51) when a wait for a peer's gradient words gave up; while it is set the
+// fused train kernel writes no parameter / moment (sticky until the host reads the status) -- see b2h_tc_status.
+__device__ int g_dp_abort = 0;
 
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int site) {
   const long long t0 = clock64();

@@ -119,22 +119,27 @@ __device__ __forceinline__ void issue_conv(uint32_t d_tmem, uint32_t a_lo, uint3
   }
 }
 
-// Grid-wide barrier of a cooperative launch (all CTAs co-resident): sense-reversing counter + generation word,
-// reusable across launches without a reset.  Bounded spin: a protocol bug ends as a wrong answer + status, not a hang.
-__device__ __forceinline__ void grid_barrier(unsigned* sync, int tid) {
+// Grid-wide barrier of a cooperative launch (all CTAs co-resident), flag form.  CTA c publishes the launch's token in
+// flag[c] of the workspace header; warp 0 of every CTA polls all flags (one coalesced load per 32 CTAs): ONE L2 round trip
+// after the last arrival (the arrival-counter form of round 1 needed three: atomicAdd, generation bump, poll).  The token
+// is header[0] + 1, read by every CTA at kernel start and written back by CTA 0 after the barrier -- stale flags of
+// earlier launches (any grid size) are always smaller.  Bounded spin: a protocol bug ends as a wrong answer + status.
+__device__ __forceinline__ void grid_barrier_flags(unsigned* hdr, unsigned tok, int tid) {
   __syncthreads();
+  volatile unsigned* flags = hdr + 4;
   if (tid == 0) {
     __threadfence();
-    volatile unsigned* gen_p = sync + 1;
-    const unsigned gen = *gen_p;
-    if (atomicAdd(sync, 1u) == gridDim.x - 1) {
-      *reinterpret_cast<volatile unsigned*>(sync) = 0u;
-      __threadfence();
-      atomicAdd(sync + 1, 1u);
-    } else {
-      const long long t0 = clock64();
-      while (*gen_p == gen) {
-        if (clock64() - t0 > 4000000000LL) { atomicExch(&g_tc_status, 50); break; }
+    flags[blockIdx.x] = tok;
+  }
+  if (tid < 32) {
+    const long long t0 = clock64();
+    for (;;) {
+      bool mine = true;
+      for (int c = tid; c < (int)gridDim.x; c += 32) mine = mine && (flags[c] == tok);
+      if (__all_sync(0xffffffffu, mine)) break;
+      if (clock64() - t0 > 4000000000LL) {
+        if (tid == 0) atomicExch(&g_tc_status, 50);
+        break;
       }
     }
     __threadfence();
@@ -142,15 +147,16 @@ __device__ __forceinline__ void grid_barrier(unsigned* sync, int tid) {
   __syncthreads();
 }
 
-__device__ __forceinline__ void adam_update(const FuseAdam& f, const Geo& g, int i, float gr, float step_size, float inv_bc2_sqrt) {
+// torch.optim.Adam single-tensor update on one element whose state (m, v, p) was loaded earlier (before the grid barrier)
+__device__ __forceinline__ void adam_apply(const FuseAdam& f, const Geo& g, const GpSlot& slot, int i, float gr, float m, float v,
+                                           float p, float step_size, float inv_bc2_sqrt) {
   gr *= f.grad_scale;
-  float m = f.m[i], v = f.v[i], p = f.params[i];
   m = fmaf(gr - m, (float)(1.0 - f.beta1), m);
   v = fmaf((float)(1.0 - f.beta2) * gr, gr, v * (float)f.beta2);
   const float denom = sqrtf(v) * inv_bc2_sqrt + f.eps;
   p = p - step_size * (m / denom);
   f.m[i] = m; f.v[i] = v; f.params[i] = p;
-  if (f.packed) scatter_packed(g, f.packed, i, p);
+  if (f.packed) scatter_packed_slot(g, f.packed, slot, p);
 }
 
 #define B2H_STAMP() do { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 120) p.dbg[dbg_n++] = clock64(); } while (0)
@@ -258,8 +264,21 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         bulk_g2s(smem + L.wd[l], p.packed + g.td_off[l], B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2, &wbar);
     }
   }
-  if (TRAIN && p.step_dev && blockIdx.x == 0 && tid == 0) *p.step_dev += 1;
-  if (TRAIN && p.epoch_dev && blockIdx.x == 0 && tid == 0) *p.epoch_dev += 1;
+  // Device-side counters.  Fused tail: every CTA reads the OLD values here (nobody writes them before the grid barrier,
+  // which needs this CTA's arrival) and CTA 0 stores old + 1 after the barrier, so the bias corrections / the exchange
+  // tag can be computed before the barrier.  Separate-launch paths: CTA 0 bumps them now for the kernels that follow.
+  long long step_next = 0, epoch_next = 0;
+  unsigned sync_tok = 0;
+  if (TRAIN) {
+    if (p.fuse.enabled) {
+      step_next = *reinterpret_cast<const volatile long long*>(p.fuse.step_dev) + 1;
+      if (p.fuse.world > 1) epoch_next = *reinterpret_cast<const volatile long long*>(p.fuse.epoch_dev) + 1;
+      sync_tok = *reinterpret_cast<const volatile unsigned*>(p.fuse.hdr) + 1u;
+    } else if (blockIdx.x == 0 && tid == 0) {
+      if (p.step_dev) *p.step_dev += 1;
+      if (p.epoch_dev) *p.epoch_dev += 1;
+    }
+  }
   {  // zero every activation / gradient buffer once: pad rows and pad channels stay zero
     const int act_bytes = L.ys;
     uint4* z = reinterpret_cast<uint4*>(smem);
@@ -291,6 +310,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
     const bool mine = co < g.cout[l];
     const int Nw = g.kp[l];
     float* lp = part + gp_layer_off(g, l);
+    float4* lp4 = reinterpret_cast<float4*>(lp);
+    const int q4 = Nw >> 2, cout_l = g.cout[l];
     const uint32_t dcol = tbase + lane_addr + kWgCol + pr * kWgPairCols;
     // column half 0 reads taps 0..2, half 1 taps 3..4 and the bias column
     const int k0 = ch == 0 ? 0 : 3, nk = ch == 0 ? 3 : 2;
@@ -305,12 +326,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         if (k >= nk) continue;
-        float4* dst = reinterpret_cast<float4*>(lp + ((size_t)(k0 + k) * g.cout[l] + co) * Nw);
+        // slot layout [k][ci/4][co][4]: for a fixed (k, q) the 16 lanes of a layer store 16 consecutive float4s
+        float4* dst = lp4 + (size_t)(k0 + k) * q4 * cout_l + co;
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           if (q * 4 < Nw)
-            dst[q] = make_float4(__uint_as_float(v[k][4 * q]), __uint_as_float(v[k][4 * q + 1]), __uint_as_float(v[k][4 * q + 2]),
-                                 __uint_as_float(v[k][4 * q + 3]));
+            dst[(size_t)q * cout_l] = make_float4(__uint_as_float(v[k][4 * q]), __uint_as_float(v[k][4 * q + 1]),
+                                                  __uint_as_float(v[k][4 * q + 2]), __uint_as_float(v[k][4 * q + 3]));
       }
       if (ch == 1) lp[B2H_KW * g.cout[l] * Nw + co] = __uint_as_float(vb[0]);
     }
@@ -655,12 +677,33 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       // ===== same launch: cross-CTA reduction (+ peer exchange) + Adam + weight re-pack =====
       const FuseAdam& f = p.fuse;
       __shared__ float s_step_size, s_inv_bc2_sqrt;
-      grid_barrier(f.sync, tid);                         // every CTA's partial slice is visible
-      B2H_STAMP();   // tail: grid barrier passed
+      const int nj = gp_total(g);                        // multiple of 4: every slice is float4-addressable
+      const int nparts = (int)gridDim.x;
+      const int per = round_up((nj + nparts - 1) / nparts, 4);
+      const int j0 = (int)blockIdx.x * per;
+      const int j_end = min(nj, j0 + per);
+      const bool dp = f.world > 1;
+      // ---- work that does not need the other CTAs, done while the slowest CTA is still on its way to the barrier:
+      // bias corrections (double-precision powers), decode of this thread's slot, its Adam state (m, v, p) ----
       if (tid == kTileThreads - 1) {                     // last thread: usually idle in the gather below
-        const long long tt = *f.step_dev;
-        s_step_size = (float)(f.lr / (1.0 - ipow(f.beta1, tt)));
-        s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - ipow(f.beta2, tt)));
+        const double lr = f.lr_dev ? *f.lr_dev : f.lr;
+        s_step_size = (float)(lr / (1.0 - ipow(f.beta1, step_next)));
+        s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - ipow(f.beta2, step_next)));
+      }
+      const bool one_pass = per <= kTileThreads;         // the usual case: one slot per thread
+      GpSlot my_slot;
+      int my_i = -1;
+      float my_m = 0.f, my_v = 0.f, my_p = 0.f;
+      if (one_pass && j0 + tid < j_end && gp_decode(g, j0 + tid, my_slot)) {
+        my_i = gp_flat_of_slot(g, my_slot);
+        my_m = __ldcg(f.m + my_i); my_v = __ldcg(f.v + my_i); my_p = __ldcg(f.params + my_i);
+      }
+      grid_barrier_flags(f.hdr, sync_tok, tid);          // every CTA's partial slice is visible
+      B2H_STAMP();   // tail: grid barrier passed
+      if (blockIdx.x == 0 && tid == 0) {                 // publish the counters for the next launch
+        *reinterpret_cast<volatile unsigned*>(f.hdr) = sync_tok;
+        *p.step_dev = step_next;
+        if (dp) *p.epoch_dev = epoch_next;
       }
       if (blockIdx.x == 0 && warp == 7 && f.loss_out) {  // loss = sum of the CTAs' loss partials (fixed order)
         float sl = 0.f;
@@ -669,17 +712,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
         if (lane == 0) *f.loss_out = sl;
       }
-      const int nj = gp_total(g);                        // multiple of 4: every slice is float4-addressable
-      const int nparts = (int)gridDim.x;
-      const int per = round_up((nj + nparts - 1) / nparts, 4);
-      const int j0 = (int)blockIdx.x * per;
-      const int j_end = min(nj, j0 + per);
-      const bool dp = f.world > 1;
-      const size_t P = (size_t)g.P;
-      const long long epoch = dp ? *f.epoch_dev : 0;
       // Data-parallel exchange buffer (per rank, peer-mapped): uint64 words [2 (epoch parity)][world (source rank)][nj],
       // each word = {fp32 gradient slot, 32-bit epoch tag} written with ONE 8-byte store ("LL" protocol): the tag
       // travels with the data, so there are no flags, no fences and no second grid barrier.
+      const long long epoch = epoch_next;
       const uint32_t tag = (uint32_t)epoch;
       const size_t ll_src = ((size_t)(epoch & 1) * f.world + f.rank) * nj;
       // Latency-bound L2 gather of this CTA's `per` slots over all CTA slices: float4 columns x part groups, 16
@@ -715,19 +751,26 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         for (int j = jb + tid; j < jn; j += kTileThreads) {
           float gr = 0.f;
           for (int pg = 0; pg < groups; ++pg) gr += red[(size_t)pg * ncol * 4 + (j - jb)];
+          bool apply = true;
           if (dp) {
-            // push my slot to every rank (remote 8-byte stores, coalesced per warp), then collect the world's slots
-            // for the same j from my own buffer and sum them in rank order (identical arithmetic on every rank).
+            // push my slot to every rank, then collect the world's slots for the same j from my own buffer and sum them
+            // in rank order (identical arithmetic on every rank).  With a multicast (NVLS) mapping of the exchange
+            // buffers ONE multimem.st is replicated by the NVSwitch into every rank's buffer; otherwise W unicast
+            // 8-byte stores (coalesced per warp, fire-and-forget over NVLink).
             const unsigned long long word = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(gr);
-            for (int r = 0; r < f.world; ++r)
-              *(reinterpret_cast<volatile unsigned long long*>(const_cast<float*>(f.peer_bufs[r])) + ll_src + j) = word;
+            if (f.mc_buf) {
+              asm volatile("multimem.st.relaxed.sys.global.b64 [%0], %1;" ::"l"(f.mc_buf + ll_src + j), "l"(word) : "memory");
+            } else {
+              for (int r = 0; r < f.world; ++r)
+                *(reinterpret_cast<volatile unsigned long long*>(const_cast<float*>(f.peer_bufs[r])) + ll_src + j) = word;
+            }
+            B2H_STAMP();   // tail: slot pushed
             float gsum = 0.f;
             const volatile unsigned long long* mine =
                 reinterpret_cast<const volatile unsigned long long*>(f.peer_bufs[f.rank]) + (size_t)(epoch & 1) * f.world * nj + j;
             const long long t0 = clock64();
             for (int rb = 0; rb < f.world; rb += 8) {
-              // up to 8 ranks' words are requested before the first one is examined: one L2 round trip for the
-              // group instead of one per rank (the serial form cost ~0.4 us per extra rank at 8 GPUs)
+              // up to 8 ranks' words are requested before the first one is examined: one L2 round trip for the group
               unsigned long long w[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u)
@@ -736,23 +779,38 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
               for (int u = 0; u < 8; ++u) {
                 if (rb + u < f.world) {
                   while ((uint32_t)(w[u] >> 32) != tag) {
-                    if (clock64() - t0 > 6000000000LL) { atomicExch(&g_tc_status, 51); break; }
+                    if (clock64() - t0 > 6000000000LL) {        // ~3 s: a peer never arrived
+                      atomicExch(&g_tc_status, 51);
+                      atomicExch(&g_dp_abort, 1);
+                      break;
+                    }
                     w[u] = mine[(size_t)(rb + u) * nj];
                   }
                   gsum += __uint_as_float((uint32_t)w[u]);       // rank order: identical arithmetic on every rank
                 }
               }
             }
-            const int i = flat_index_of_gp(g, j);
-            if (i >= 0) adam_update(f, g, i, gsum, s_step_size, s_inv_bc2_sqrt);
-          } else {
-            const int i = flat_index_of_gp(g, j);
-            if (i >= 0) adam_update(f, g, i, gr, s_step_size, s_inv_bc2_sqrt);
+            B2H_STAMP();   // tail: world's slots collected
+            gr = gsum;
+            // Sticky abort: after a peer timeout NO parameter / moment is written (this step and every later one, until
+            // the host has read and cleared the status) -- replicas may stall, they never silently diverge.
+            apply = *reinterpret_cast<volatile int*>(&g_dp_abort) == 0;
+          }
+          if (apply) {
+            if (one_pass) {
+              if (my_i >= 0) adam_apply(f, g, my_slot, my_i, gr, my_m, my_v, my_p, s_step_size, s_inv_bc2_sqrt);
+            } else {
+              GpSlot sl;
+              if (gp_decode(g, j, sl)) {
+                const int i = gp_flat_of_slot(g, sl);
+                adam_apply(f, g, sl, i, gr, f.m[i], f.v[i], f.params[i], s_step_size, s_inv_bc2_sqrt);
+              }
+            }
           }
         }
         __syncthreads();
       }
-      B2H_STAMP();   // tail: reduction (+ Adam when single-GPU) done
+      B2H_STAMP();   // tail: reduction (+ exchange) + Adam done
     }
   }
   if (!TRAIN && tid == 0) bulk_wait0();
@@ -804,12 +862,7 @@ int launch_tc_tile(TcTileArgs& p, bool train, cudaStream_t stream) {
   const int nt2 = p.NT == 2 ? 1 : 0;
   const void* fn = train ? (nt2 ? (const void*)conv_tc_tile_kernel<true, 2> : (const void*)conv_tc_tile_kernel<true, 1>)
                          : (nt2 ? (const void*)conv_tc_tile_kernel<false, 2> : (const void*)conv_tc_tile_kernel<false, 1>);
-  static size_t attr_bytes[2][2] = {{0, 0}, {0, 0}};
-  if (smem > attr_bytes[train ? 1 : 0][nt2]) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e)); return B2H_ECUDA; }
-    attr_bytes[train ? 1 : 0][nt2] = smem;
-  }
+  if (int rc = ensure_dyn_smem(fn, smem)) return rc;
   void* kargs[] = {&p};
   cudaError_t le;
   if (train && p.fuse.enabled)   // grid barriers inside: cooperative launch guarantees that all CTAs (<= 1 per SM) are co-resident

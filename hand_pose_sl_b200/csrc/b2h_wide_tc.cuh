@@ -354,12 +354,7 @@ int launch_tc_wide_fwd(const void* x, int x_dtype, const float* params, const ch
   if (S < 3) { set_error("wide tensor-core forward: C=%d leaves no room for the weight ring", g.C); return B2H_ESHAPE; }
   p.nstage = S;
   const size_t smem = (size_t)p.a_bytes + (size_t)S * kWideStage;
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_wide_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { cudaGetLastError(); set_error("cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(e)); return B2H_ECUDA; }
-    attr_bytes = smem;
-  }
+  if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_wide_fwd_kernel), smem)) return rc;
   int grid = num_sms();
   if (grid > p.n_tiles) grid = p.n_tiles;
   // weight tensor map: the forward UMMA sections [tf_off[0], td_off[0]) as rows of 64 bf16 (128 B), box = 64 rows

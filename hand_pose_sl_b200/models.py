@@ -33,6 +33,21 @@ class LinearPositionalEmbedding(nn.Module):
         self.max_len = max_len
         self.pe = (torch.arange(max_len).float() / max_len)[None, None, :]
 
+    def forward(self, inp, lengths=None):
+        """(B, C, T) -> (B, C+1, T): the constant row t/max_len in front of the channels (HandPoseModels.py:78-84;
+        `lengths` is accepted and ignored exactly like the reference).  One CUDA launch; like the reference's
+        torch.cat it raises unless T == max_len."""
+        _lib.require_device(inp, "LinearPositionalEmbedding input")
+        if inp.dim() != 3:
+            raise RuntimeError(f"LinearPositionalEmbedding expects (B, C, T), got {tuple(inp.shape)}")
+        B, Cc, T = inp.shape
+        if T != self.max_len:
+            raise RuntimeError(f"Sizes of tensors must match except in dimension 1. Expected size {self.max_len} but got size {T}")
+        x = inp.to(torch.float32).contiguous()
+        out = torch.empty((B, Cc + 1, T), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().b2h_pos_emb_concat(_lib.ptr(x), _lib.ptr(out), B, Cc, T, self.max_len, _lib.stream_ptr(x.device)))
+        return out
+
 
 class _ConvForward(torch.autograd.Function):
     @staticmethod

@@ -13,6 +13,7 @@ import torch.distributed as dist
 
 from . import _lib
 from .models import ConvModel
+from .runner import _StepBuffers
 from .steps import FusedAdam
 
 
@@ -62,9 +63,9 @@ def broadcast_parameters(model: ConvModel, src: int = 0, group=None):
 
 
 def _symmetric_exchange_buffer(n_floats: int, device, group):
-    """Peer-mapped buffer [2][P] fp32 gradients + [world] int64 flags on every rank (torch symmetric memory:
-    cuMem allocations mapped into every peer over NVLink).  Returns (local tensor, device array of peer base
-    pointers indexed by rank)."""
+    """Peer-mapped exchange buffer on every rank (torch symmetric memory: cuMem allocations mapped into every peer over
+    NVLink, plus -- when the fabric supports it -- one multicast (NVLS) address that reaches all of them).  Returns
+    (local tensor, handle, device array of peer base pointers indexed by rank, multicast address or 0)."""
     import torch.distributed._symmetric_memory as symm_mem
     world = dist.get_world_size(group)
     buf = symm_mem.empty(n_floats, dtype=torch.float32, device=device)
@@ -73,56 +74,46 @@ def _symmetric_exchange_buffer(n_floats: int, device, group):
     ptrs = [int(p) for p in hdl.buffer_ptrs]
     if len(ptrs) != world or hdl.rank != dist.get_rank(group):
         raise RuntimeError("symmetric memory rendezvous returned an unexpected peer table")
+    mc = 0
+    try:
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+    except Exception:  # noqa: BLE001
+        mc = 0
     torch.cuda.synchronize(device)
     dist.barrier(group)                                   # every rank's buffer is zeroed before anyone signals
-    return buf, hdl, torch.tensor(ptrs, dtype=torch.int64, device=device)
+    return buf, hdl, torch.tensor(ptrs, dtype=torch.int64, device=device), mc
 
 
-class DataParallelTrainer:
-    """One process per GPU.  exchange="p2p" (default when symmetric memory is available): step() = [forward+mask+
-    loss+backward kernel, partial-reduce kernel -> peer-mapped buffer] -> [ONE kernel: flag exchange with all peers,
-    sum of the peers' gradients over NVLink, Adam + re-pack] -- the collective is fused with the optimiser, no NCCL
-    call on the step path.  exchange="nccl": ... -> dist.all_reduce(flat grads) -> Adam kernel (baseline).
-    Static buffers; the whole step can be captured in a CUDA graph either way."""
+class DataParallelTrainer(_StepBuffers):
+    """One process per GPU.  exchange="p2p" (default when symmetric memory is available): step() = ONE cooperative
+    launch per rank in bf16 mode -- forward+mask+loss+backward, cross-CTA reduction, push of the reduced gradient
+    words into every peer's exchange buffer over NVLink (one multimem.st per slot through the NVSwitch when a multicast
+    mapping exists, `multicast=True`), sum in rank order, Adam + re-pack; no NCCL call on the step path.
+    exchange="nccl": ... -> dist.all_reduce(flat grads) -> Adam kernel (baseline).
+    Static buffers; the whole step can be captured in a CUDA graph either way.  A peer that never delivers is a
+    device-side timeout: parameter updates stop and `finish()` / `check_status()` raise."""
 
     def __init__(self, model: ConvModel, optimizer: FusedAdam, B: int, T: int, loss: str = "L1", group=None,
-                 n_slots: int = 1, exchange: str = "auto"):
-        self.model, self.opt, self.B, self.T, self.loss_name, self.group = model, optimizer, B, T, loss, group
-        self.kind = _lib.LOSSES[loss]
+                 n_slots: int = 1, exchange: str = "auto", x_dtype=None, multicast: bool = True):
+        self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        flat = model.flat_parameters()
-        self.dev = flat.device
-        _lib.require_device(flat, "model")
-        _lib.require_sm100(self.dev)
         broadcast_parameters(model, 0, group)
-        g = optimizer.param_groups[0]
-        if optimizer._owner(g) is not model:
-            raise RuntimeError("DataParallelTrainer needs FusedAdam(model.parameters()) over exactly this model")
-        self.state = optimizer._group_state(0, g, model)
-        K = model.n_in // 2
+        self._init_buffers(model, optimizer, B, T, loss, n_slots, x_dtype)
         dev = self.dev
-        self.n_slots = n_slots
-        self.x = torch.zeros((n_slots, B, T, K, 2), dtype=torch.float32, device=dev)
-        self.target = torch.zeros((n_slots, B, T, 21, 2), dtype=torch.float32, device=dev)
-        self.conf = torch.zeros((n_slots, B, T, 21), dtype=torch.float32, device=dev) if self.kind == _lib.LOSS_CONFL1 else None
-        self.lengths = torch.full((n_slots, B), T, dtype=torch.int32, device=dev)
-        self.loss = torch.zeros((n_slots,), dtype=torch.float32, device=dev)
-        self.grads = torch.zeros_like(flat)
-        self.step_dev = torch.full((1,), int(self.state["step"]), dtype=torch.int64, device=dev)
-        self.ws = model.workspace(B, T)
-        self.packed = model.packed_weights()
-        self.lib = _lib.load()
-        self.host_steps = int(self.state["step"])
-        self.graph, self._graph_steps = None, 0
+        self.grads = torch.zeros_like(model.flat_parameters())
         if exchange not in ("auto", "p2p", "nccl"):
             raise ValueError("exchange must be 'auto', 'p2p' or 'nccl'")
         self.exchange = "nccl"
         self.sym = self.sym_hdl = self.peer_ptrs = None
+        self.mc_ptr = 0
+        self.peers_seen = self.world
         if self.world > 1 and exchange in ("auto", "p2p"):
             try:
                 n_in_, C_, pe_ = model._geometry()
                 nfl = int(self.lib.b2h_dp_exchange_floats(n_in_, C_, pe_, self.world))
-                self.sym, self.sym_hdl, self.peer_ptrs = _symmetric_exchange_buffer(nfl, dev, group)
+                self.sym, self.sym_hdl, self.peer_ptrs, mc = _symmetric_exchange_buffer(nfl, dev, group)
+                self.mc_ptr = mc if multicast else 0
+                self.peers_seen = int(self.peer_ptrs.numel())
                 self.epoch_dev = torch.zeros((1,), dtype=torch.int64, device=dev)
                 self.rank = dist.get_rank(group)
                 self.exchange = "p2p"
@@ -132,14 +123,8 @@ class DataParallelTrainer:
                 import warnings
                 warnings.warn(f"symmetric-memory gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
 
-    def load(self, batch, slot=0, non_blocking=True):
-        self.x[slot].copy_(batch["input_kp"], non_blocking=non_blocking)
-        self.target[slot].copy_(batch["target_kp"], non_blocking=non_blocking)
-        if self.conf is not None:
-            self.conf[slot].copy_(batch["target_conf"], non_blocking=non_blocking)
-        self.lengths[slot].copy_(batch["n_frames"], non_blocking=non_blocking)
-
     def step(self, slot=0):
+        self._sync_host_state()
         m, g = self.model, self.opt.param_groups[0]
         n_in, C, pe = m._geometry()
         b1, b2 = g["betas"]
@@ -147,58 +132,37 @@ class DataParallelTrainer:
         sp = _lib.stream_ptr(self.dev)
         if self.exchange == "p2p":
             _lib.check(self.lib.b2h_train_step_dp(
-                _lib.ptr(self.x[slot]), _lib.DT_F32, _lib.ptr(self.target[slot]), _lib.ptr(conf), _lib.ptr(self.lengths[slot]),
+                _lib.ptr(self.x[slot]), self._x_dt(), _lib.ptr(self.target[slot]), _lib.ptr(conf), _lib.ptr(self.lengths[slot]),
                 _lib.ptr(m._flat), _lib.ptr(self.packed), _lib.ptr(self.state["m"]), _lib.ptr(self.state["v"]),
                 _lib.ptr(self.loss[slot:slot + 1]), self.B, self.T, n_in, C, pe, self.kind, _lib.PRECISIONS[m.precision],
-                float(g["lr"]), b1, b2, g["eps"], _lib.ptr(self.step_dev), _lib.ptr(self.epoch_dev), _lib.ptr(self.sym),
-                _lib.ptr(self.peer_ptrs), self.rank, self.world, grad_scale_for(self.loss_name, self.world),
-                _lib.ptr(self.ws), self.ws.numel(), sp))
-            self.host_steps += 1
-            self.state["step"] = self.host_steps
+                float(g["lr"]), b1, b2, g["eps"], _lib.ptr(self.step_dev), _lib.ptr(self.epoch_dev), _lib.ptr(self.lr_dev),
+                _lib.ptr(self.sym), _lib.ptr(self.peer_ptrs), (self.mc_ptr or None), self.rank, self.world,
+                grad_scale_for(self.loss_name, self.world), _lib.ptr(self.ws), self.ws.numel(), sp))
+            self._advance(1)
             return self.loss[slot]
         _lib.check(self.lib.b2h_train_forward_backward(
-            _lib.ptr(self.x[slot]), _lib.DT_F32, _lib.ptr(self.target[slot]), _lib.ptr(conf), _lib.ptr(self.lengths[slot]),
+            _lib.ptr(self.x[slot]), self._x_dt(), _lib.ptr(self.target[slot]), _lib.ptr(conf), _lib.ptr(self.lengths[slot]),
             _lib.ptr(m._flat), _lib.ptr(self.packed), _lib.ptr(self.grads), _lib.ptr(self.loss[slot:slot + 1]), None,
             self.B, self.T, n_in, C, pe, self.kind, _lib.PRECISIONS[m.precision], _lib.ptr(self.step_dev),
             _lib.ptr(self.ws), self.ws.numel(), sp))
         allreduce_flat(self.grads, self.group)
         _lib.check(self.lib.b2h_adam_step(
             _lib.ptr(m._flat), _lib.ptr(self.grads), _lib.ptr(self.state["m"]), _lib.ptr(self.state["v"]), m._flat.numel(),
-            float(g["lr"]), b1, b2, g["eps"], 0, _lib.ptr(self.step_dev), grad_scale_for(self.loss_name, self.world),
-            _lib.ptr(self.packed), n_in, C, pe, sp))
-        self.host_steps += 1
-        self.state["step"] = self.host_steps
+            float(g["lr"]), b1, b2, g["eps"], 0, _lib.ptr(self.step_dev), _lib.ptr(self.lr_dev),
+            grad_scale_for(self.loss_name, self.world), _lib.ptr(self.packed), n_in, C, pe, sp))
+        self._advance(1)
         return self.loss[slot]
 
-    def capture(self, n_steps=None):
-        n_steps = n_steps or self.n_slots
-        torch.cuda.synchronize(self.dev)
-        saved = (self.host_steps, self.step_dev.clone(), self.model._flat.clone(), self.state["m"].clone(), self.state["v"].clone())
-        s = torch.cuda.Stream(self.dev)
-        s.wait_stream(torch.cuda.current_stream(self.dev))
-        with torch.cuda.stream(s):
-            for i in range(3):
-                self.step(i % self.n_slots)
-        torch.cuda.current_stream(self.dev).wait_stream(s)
-        torch.cuda.synchronize(self.dev)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for i in range(n_steps):
-                self.step(i % self.n_slots)
-        self.host_steps = saved[0]
-        self.step_dev.copy_(saved[1]); self.model._flat.copy_(saved[2])
-        self.state["m"].copy_(saved[3]); self.state["v"].copy_(saved[4])
-        self.model.mark_packed_stale(); self.packed = self.model.packed_weights()
-        self.state["step"] = self.host_steps
-        torch.cuda.synchronize(self.dev)
-        self.graph, self._graph_steps = g, n_steps
-        return g
+    def replica_checksum(self):
+        """(sum, sum of squares) of the flat parameters in float64 -- equal on every rank iff the replicas are
+        bit-identical for all practical purposes; `replicas_identical()` all-gathers and compares the raw bits."""
+        flat = self.model.flat_parameters().double()
+        return torch.stack([flat.sum(), (flat * flat).sum()])
 
-    def replay(self):
-        self.graph.replay()
-        self.host_steps += self._graph_steps
-        self.state["step"] = self.host_steps
-
-    def finish(self):
-        self.state["step_t"].fill_(float(self.host_steps))
-        self.model.packed_weights(fresh_from_kernel=True)
+    def replicas_identical(self):
+        flat = self.model.flat_parameters()
+        if self.world == 1:
+            return True
+        gathered = [torch.empty_like(flat) for _ in range(self.world)]
+        dist.all_gather(gathered, flat.contiguous(), group=self.group)
+        return all(torch.equal(gathered[0], t) for t in gathered[1:])

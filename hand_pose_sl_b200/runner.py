@@ -1,8 +1,14 @@
 """Low-overhead steady-state runners: static device buffers, pre-bound C-ABI arguments, optional CUDA
-graph capture.  The fused train step is two kernel launches (~µs of GPU time at the reference's batch
+graph capture.  The fused train step is ONE cooperative launch (~25 µs of GPU time at the reference's batch
 sizes), so the per-call Python/torch bookkeeping of the modular API would dominate; these runners are
 what a training / serving loop uses once shapes are fixed (launch latency, not the
-tensor pipe or HBM, bounds every BASELINE config)."""
+tensor pipe or HBM, bounds every BASELINE config).
+
+Input staging: every slot is ONE contiguous device buffer  [input_kp | target_kp | target_conf? | n_frames(int32)]
+and `host_stage(batch)` builds the same layout in pinned host memory, so a step's inputs travel with ONE
+cudaMemcpyAsync (`load_staged`).  With `x_dtype=torch.bfloat16` the keypoint input is shipped as bf16 -- the bf16
+kernels round it to bf16 on the way into shared memory anyway (cvt.rn == torch's CPU rounding), so the result is
+bit-identical and the copy is 0.8 MB shorter at batch 256 x 64."""
 from __future__ import annotations
 
 import torch
@@ -12,13 +18,16 @@ from .models import ConvModel
 from .steps import FusedAdam
 
 
-class TrainStepRunner:
-    """steps/traintest.py:94-121 for a fixed (B, T): `load(batch)` copies a batch into the static
-    buffers, `step()` enqueues forward+mask+loss+backward and reduce+Adam+repack (2 launches).
-    The Adam step counter lives on the device so a captured graph can be replayed."""
+def _align(n, a=256):
+    return (n + a - 1) // a * a
 
-    def __init__(self, model: ConvModel, optimizer: FusedAdam, B: int, T: int, loss: str = "L1", n_slots: int = 1):
+
+class _StepBuffers:
+    """Static per-slot buffers shared by TrainStepRunner and parallel.DataParallelTrainer."""
+
+    def _init_buffers(self, model: ConvModel, optimizer: FusedAdam, B: int, T: int, loss: str, n_slots: int, x_dtype):
         self.model, self.opt, self.B, self.T = model, optimizer, B, T
+        self.loss_name = loss
         self.kind = _lib.LOSSES[loss]
         flat = model.flat_parameters()
         dev = flat.device
@@ -27,56 +36,123 @@ class TrainStepRunner:
         self.dev = dev
         group = optimizer.param_groups[0]
         if optimizer._owner(group) is not model:
-            raise RuntimeError("TrainStepRunner needs FusedAdam(model.parameters()) over exactly this model")
+            raise RuntimeError(f"{type(self).__name__} needs FusedAdam(model.parameters()) over exactly this model")
         self.state = optimizer._group_state(0, group, model)
         K = model.n_in // 2
         self.n_slots = n_slots
-        self.x = torch.zeros((n_slots, B, T, K, 2), dtype=torch.float32, device=dev)
-        self.target = torch.zeros((n_slots, B, T, 21, 2), dtype=torch.float32, device=dev)
-        self.conf = torch.zeros((n_slots, B, T, 21), dtype=torch.float32, device=dev) if self.kind == _lib.LOSS_CONFL1 else None
-        self.lengths = torch.full((n_slots, B), T, dtype=torch.int32, device=dev)
+        x_dtype = x_dtype or torch.float32
+        if x_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("x_dtype must be torch.float32 or torch.bfloat16")
+        if x_dtype == torch.bfloat16 and model.precision != "bf16":
+            raise ValueError("bf16 inputs are only bit-identical to fp32 inputs in bf16 mode")
+        self.x_dtype = x_dtype
+        esz = 2 if x_dtype == torch.bfloat16 else 4
+        # byte layout of one slot (every section 256-B aligned)
+        self._sec = {}
+        off = 0
+        for name, nbytes in (("x", B * T * K * 2 * esz), ("target", B * T * 42 * 4),
+                             ("conf", B * T * 21 * 4 if self.kind == _lib.LOSS_CONFL1 else 0), ("lengths", B * 4)):
+            self._sec[name] = (off, nbytes)
+            off = _align(off + nbytes)
+        self.slot_bytes = off
+        self.stage = torch.zeros((n_slots, self.slot_bytes), dtype=torch.uint8, device=dev)
+
+        def view(name, dtype, shape):
+            o, n = self._sec[name]
+            return self.stage[:, o:o + n].view(dtype).view((n_slots,) + shape)
+
+        self.x = view("x", x_dtype, (B, T, K, 2))
+        self.target = view("target", torch.float32, (B, T, 21, 2))
+        self.conf = view("conf", torch.float32, (B, T, 21)) if self.kind == _lib.LOSS_CONFL1 else None
+        self.lengths = view("lengths", torch.int32, (B,))
+        self.lengths.fill_(T)
         self.loss = torch.zeros((n_slots,), dtype=torch.float32, device=dev)
-        self.step_dev = torch.full((1,), int(self.state["step"]), dtype=torch.int64, device=dev)
+        # Adam step counter and learning rate in device memory, owned by the optimiser state and shared by every runner
+        # on it: a captured graph advances the counter itself and follows adjust_learning_rate (traintest.py:83-84)
+        self.step_dev = self.state["step_dev"]
+        self.lr_dev = self.state["lr_dev"]
         self.ws = model.workspace(B, T)
         self.packed = model.packed_weights()
         self.lib = _lib.load()
         self.graph = None
         self._graph_steps = 0
-        self.host_steps = int(self.state["step"])
 
+    @property
+    def host_steps(self):
+        return int(self.state["step"])
+
+    def _advance(self, n):
+        self.state["step"] += n
+        self.state["dev_step_mirror"] = self.state["step"]
+
+    # ------------------------------------------------------------------ inputs
     def load(self, batch, slot=0, non_blocking=True):
-        """Copy one reference-style batch dict (CPU pinned or device tensors) into slot `slot`."""
+        """Copy one reference-style batch dict (CPU pinned or device tensors) into slot `slot` (one copy per tensor;
+        `load_staged` moves the same bytes with a single copy)."""
         self.x[slot].copy_(batch["input_kp"], non_blocking=non_blocking)
         self.target[slot].copy_(batch["target_kp"], non_blocking=non_blocking)
         if self.conf is not None:
             self.conf[slot].copy_(batch["target_conf"], non_blocking=non_blocking)
         self.lengths[slot].copy_(batch["n_frames"], non_blocking=non_blocking)
 
-    def step(self, slot=0):
-        """Enqueue one training step on the current stream; returns the 0-dim device loss tensor."""
-        m, g = self.model, self.opt.param_groups[0]
-        n_in, C, pe = m._geometry()
-        b1, b2 = g["betas"]
-        conf = None if self.conf is None else self.conf[slot]
-        _lib.check(self.lib.b2h_train_step(
-            _lib.ptr(self.x[slot]), _lib.DT_F32, _lib.ptr(self.target[slot]), _lib.ptr(conf), _lib.ptr(self.lengths[slot]),
-            _lib.ptr(m._flat), _lib.ptr(self.packed), _lib.ptr(self.state["m"]), _lib.ptr(self.state["v"]),
-            _lib.ptr(self.loss[slot:slot + 1]), self.B, self.T, n_in, C, pe, self.kind, _lib.PRECISIONS[m.precision],
-            float(g["lr"]), b1, b2, g["eps"], 0, _lib.ptr(self.step_dev), _lib.ptr(self.ws), self.ws.numel(),
-            _lib.stream_ptr(self.dev)))
-        self.host_steps += 1
-        self.state["step"] = self.host_steps
-        return self.loss[slot]
+    def host_stage(self, batch, out=None):
+        """Pack a reference-style batch dict (CPU tensors) into ONE pinned host buffer with the slot's byte layout
+        (the collate step of a data loader).  Returns the uint8 tensor `load_staged` takes."""
+        if out is None:
+            out = torch.zeros(self.slot_bytes, dtype=torch.uint8).pin_memory()
+
+        def put(name, t, dtype):
+            o, n = self._sec[name]
+            out[o:o + n].view(dtype).copy_(t.reshape(-1))
+
+        put("x", batch["input_kp"], self.x_dtype)
+        put("target", batch["target_kp"], torch.float32)
+        if self.conf is not None:
+            put("conf", batch["target_conf"], torch.float32)
+        put("lengths", torch.as_tensor(batch["n_frames"]), torch.int32)
+        return out
+
+    def load_staged(self, staged, slot=0, non_blocking=True):
+        """ONE host -> device copy of a `host_stage` buffer into slot `slot`."""
+        self.stage[slot].copy_(staged, non_blocking=non_blocking)
+
+    # ------------------------------------------------------------------ bookkeeping shared by step()/replay()
+    def _sync_host_state(self):
+        """Before enqueuing (never while capturing): follow a changed learning rate and out-of-band weight edits."""
+        if torch.cuda.is_current_stream_capturing():
+            return
+        st = self.state
+        lr = float(self.opt.param_groups[0]["lr"])
+        if lr != st["lr_mirror"]:
+            self.lr_dev.fill_(lr)
+            st["lr_mirror"] = lr
+        if st["dev_step_mirror"] != st["step"]:          # the modular optimiser path stepped in between
+            self.step_dev.fill_(int(st["step"]))
+            st["dev_step_mirror"] = st["step"]
+        self.packed = self.model.packed_weights()        # cheap version compare; re-packs after load_state_dict etc.
+
+    def _x_dt(self):
+        return _lib.DT_BF16 if self.x_dtype == torch.bfloat16 else _lib.DT_F32
+
+    def check_status(self):
+        """Raise if a device-side wait gave up (grid barrier, MMA completion, data-parallel peer wait).  Synchronises."""
+        tc = int(self.lib.b2h_tc_status())
+        dp = int(self.lib.b2h_dp_status())
+        if tc or dp:
+            raise _lib.B2HError(f"device-side wait timed out (tc_status={tc}, dp_status={dp}): "
+                                + ("a data-parallel peer never delivered its gradients; parameter updates were suppressed "
+                                   "from that step on" if tc == 51 or dp else "kernel protocol error"))
 
     def capture(self, n_steps=None):
         """Capture `n_steps` consecutive steps (slot i % n_slots) into one CUDA graph."""
         n_steps = n_steps or self.n_slots
         torch.cuda.synchronize(self.dev)
-        saved = (self.host_steps, self.step_dev.clone(), self.model._flat.clone(), self.state["m"].clone(), self.state["v"].clone())
+        self._sync_host_state()
+        saved = (int(self.state["step"]), self.step_dev.clone(), self.model._flat.clone(), self.state["m"].clone(), self.state["v"].clone())
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
-            for i in range(2):                       # warm-up outside capture (lazy module load, attributes)
+            for i in range(3):                       # warm-up outside capture (lazy module load, attributes)
                 self.step(i % self.n_slots)
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
@@ -85,32 +161,59 @@ class TrainStepRunner:
             for i in range(n_steps):
                 self.step(i % self.n_slots)
         # undo the warm-up / capture bookkeeping: graphs only record, they do not execute
-        self.host_steps = saved[0]
+        self.state["step"] = self.state["dev_step_mirror"] = saved[0]
         self.step_dev.copy_(saved[1]); self.model._flat.copy_(saved[2])
         self.state["m"].copy_(saved[3]); self.state["v"].copy_(saved[4])
         self.model.mark_packed_stale(); self.packed = self.model.packed_weights()
-        self.state["step"] = self.host_steps
         torch.cuda.synchronize(self.dev)
         self.graph, self._graph_steps = g, n_steps
         return g
 
     def replay(self):
+        self._sync_host_state()
         self.graph.replay()
-        self.host_steps += self._graph_steps
-        self.state["step"] = self.host_steps
+        self._advance(self._graph_steps)
 
     def finish(self):
-        """Publish the step count to the optimiser's torch-layout state (for state_dict())."""
+        """Publish the step count to the optimiser's torch-layout state (for state_dict()) and surface any
+        device-side timeout."""
         self.state["step_t"].fill_(float(self.host_steps))
         self.model.packed_weights(fresh_from_kernel=True)
+        self.check_status()
 
 
-def pipelined_steps(runner, batches):
+class TrainStepRunner(_StepBuffers):
+    """steps/traintest.py:94-121 for a fixed (B, T): `load(batch)` / `load_staged(buf)` copies a batch into the static
+    buffers, `step()` enqueues forward+mask+loss+backward+reduce+Adam+repack (bf16 mode: ONE cooperative launch).
+    The Adam step counter and the learning rate live on the device so a captured graph can be replayed."""
+
+    def __init__(self, model: ConvModel, optimizer: FusedAdam, B: int, T: int, loss: str = "L1", n_slots: int = 1, x_dtype=None):
+        self._init_buffers(model, optimizer, B, T, loss, n_slots, x_dtype)
+
+    def step(self, slot=0):
+        """Enqueue one training step on the current stream; returns the 0-dim device loss tensor."""
+        self._sync_host_state()
+        m, g = self.model, self.opt.param_groups[0]
+        n_in, C, pe = m._geometry()
+        b1, b2 = g["betas"]
+        conf = None if self.conf is None else self.conf[slot]
+        _lib.check(self.lib.b2h_train_step(
+            _lib.ptr(self.x[slot]), self._x_dt(), _lib.ptr(self.target[slot]), _lib.ptr(conf), _lib.ptr(self.lengths[slot]),
+            _lib.ptr(m._flat), _lib.ptr(self.packed), _lib.ptr(self.state["m"]), _lib.ptr(self.state["v"]),
+            _lib.ptr(self.loss[slot:slot + 1]), self.B, self.T, n_in, C, pe, self.kind, _lib.PRECISIONS[m.precision],
+            float(g["lr"]), b1, b2, g["eps"], 0, _lib.ptr(self.step_dev), _lib.ptr(self.lr_dev), _lib.ptr(self.ws),
+            self.ws.numel(), _lib.stream_ptr(self.dev)))
+        self._advance(1)
+        return self.loss[slot]
+
+
+def pipelined_steps(runner, batches, status_every=0):
     """Training loop with a double-buffered input pipeline (what a DataLoader with prefetch gives the reference loop,
     steps/traintest.py:87-123): while step i runs, batch i+1 travels host -> device on a copy stream into the other
-    slot.  `runner` is a TrainStepRunner or parallel.DataParallelTrainer with n_slots >= 2; `batches` yields
-    reference-style batch dicts in pinned host memory.  Yields the loss of every step as a float (device -> host
-    read, traintest.py:123), so each step's result is observed before the next one is enqueued."""
+    slot.  `runner` is a TrainStepRunner or parallel.DataParallelTrainer with n_slots >= 2; `batches` yields either
+    `runner.host_stage(...)` buffers (ONE copy per step) or reference-style batch dicts in pinned host memory.
+    Yields the loss of every step as a float (device -> host read, traintest.py:123), so each step's result is
+    observed before the next one is enqueued."""
     if runner.n_slots < 2:
         raise RuntimeError("pipelined_steps needs a runner with n_slots >= 2")
     dev = runner.x.device
@@ -126,7 +229,10 @@ def pipelined_steps(runner, batches):
         if used[s]:
             copy_stream.wait_event(freed[s])             # do not overwrite a slot a step is still reading
         with torch.cuda.stream(copy_stream):
-            runner.load(batch, slot=s)
+            if isinstance(batch, torch.Tensor):
+                runner.load_staged(batch, slot=s)
+            else:
+                runner.load(batch, slot=s)
             ready[s].record(copy_stream)
 
     nxt = next(it, None)
@@ -144,6 +250,8 @@ def pipelined_steps(runner, batches):
         freed[s].record(main)
         used[s] = True
         yield float(loss.item())
+        if status_every and (i + 1) % status_every == 0:
+            runner.check_status()
         if nxt is None:
             return
         i += 1
@@ -170,6 +278,8 @@ class ForwardRunner:
 
     def run(self, slot=0):
         m = self.model
+        if not torch.cuda.is_current_stream_capturing():
+            self.packed = m.packed_weights()             # follows load_state_dict / optimiser updates (version compare)
         n_in, C, pe = m._geometry()
         _lib.check(self.lib.b2h_conv_forward(
             _lib.ptr(self.x[slot]), _lib.DT_BF16 if self.x.dtype == torch.bfloat16 else _lib.DT_F32, _lib.ptr(m._flat),
@@ -192,3 +302,9 @@ class ForwardRunner:
                 self.run(i % self.n_slots)
         self.graph = g
         return g
+
+    def replay(self):
+        """Replay the captured graph; weights changed since capture (load_state_dict, training) are re-packed first
+        (the packed buffer keeps its address, so the captured launches see them)."""
+        self.packed = self.model.packed_weights()
+        self.graph.replay()

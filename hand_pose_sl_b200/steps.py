@@ -176,7 +176,12 @@ class FusedAdam(torch.optim.Optimizer):
                     step = int(ps["step"]) if "step" in ps else step
                 off += n
             step_t = torch.tensor(float(step))      # ONE host tensor shared by the 8 per-parameter states
-            st = {"m": m, "v": v, "step": step, "step_t": step_t}
+            # device-side step counter + learning rate, shared by every runner built on this optimiser (a captured
+            # graph advances / reads them on the device); "dev_step_mirror" = the value the host believes is in step_dev
+            st = {"m": m, "v": v, "step": step, "step_t": step_t,
+                  "step_dev": torch.full((1,), step, dtype=torch.int64, device=flat.device), "dev_step_mirror": step,
+                  "lr_dev": torch.full((1,), float(group["lr"]), dtype=torch.float64, device=flat.device),
+                  "lr_mirror": float(group["lr"])}
             self._flat_state[gi] = st
             off = 0
             for p in group["params"]:
@@ -215,7 +220,7 @@ class FusedAdam(torch.optim.Optimizer):
                 packed = model.packed_weights()
                 _lib.check(lib.b2h_adam_step(_lib.ptr(flat), _lib.ptr(fg), _lib.ptr(st["m"]), _lib.ptr(st["v"]),
                                              flat.numel(), float(group["lr"]), b1, b2, group["eps"], st["step"],
-                                             None, float(grad_scale), _lib.ptr(packed), n_in, C, pe,
+                                             None, None, float(grad_scale), _lib.ptr(packed), n_in, C, pe,
                                              _lib.stream_ptr(flat.device)))
                 model.packed_weights(fresh_from_kernel=True)
                 st["step_t"].fill_(float(st["step"]))
@@ -233,7 +238,7 @@ class FusedAdam(torch.optim.Optimizer):
                     g = p.grad.contiguous()
                     _lib.check(lib.b2h_adam_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(s["exp_avg"]), _lib.ptr(s["exp_avg_sq"]),
                                                  p.numel(), float(group["lr"]), b1, b2, group["eps"], int(s["step"]),
-                                                 None, float(grad_scale), None, 0, 0, 0, _lib.stream_ptr(p.device)))
+                                                 None, None, float(grad_scale), None, 0, 0, 0, _lib.stream_ptr(p.device)))
                     owner = owner_of(p)
                     if owner is not None:
                         owner.mark_packed_stale()
@@ -270,7 +275,7 @@ def fused_train_step(model: ConvModel, batch, optimizer: FusedAdam, loss="L1"):
                                   _lib.ptr(conf), _lib.ptr(len32), _lib.ptr(flat), _lib.ptr(packed), _lib.ptr(st["m"]),
                                   _lib.ptr(st["v"]), _lib.ptr(loss_out), B, T, n_in, C, pe, kind,
                                   _lib.PRECISIONS[model.precision], float(group["lr"]), b1, b2, group["eps"], st["step"],
-                                  None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
+                                  None, None, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)))
     model.packed_weights(fresh_from_kernel=True)
     st["step_t"].fill_(float(st["step"]))
     return loss_out

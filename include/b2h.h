@@ -56,8 +56,11 @@ int64_t b2h_param_count(int n_in, int C, int pos_emb);
 int64_t b2h_param_offset(int n_in, int C, int pos_emb, int layer, int is_bias);
 /* bytes of the extension-owned packed weight buffer (fp32 tap-major + bf16 UMMA operand layouts) */
 int64_t b2h_packed_bytes(int n_in, int C, int pos_emb);
-/* bytes of scratch the train entry points need (per-CTA gradient partials for a deterministic
- * two-stage reduction + loss partials) */
+/* Host-only self-check of the internal gradient-partial slot layout of the tensor-core train kernel (flat parameter
+ * index <-> slot bijection, padding slots, float4 alignment); returns the number of violations, 0 = consistent. */
+int64_t b2h_gp_layout_check(int n_in, int C, int pos_emb);
+/* bytes of scratch the train entry points need (1-KB header of the fused kernel's grid barrier + per-CTA gradient
+ * partials for a deterministic two-stage reduction + loss partials); 16-byte aligned, zeroed once at allocation */
 int64_t b2h_workspace_bytes(int B, int T, int n_in, int C, int pos_emb, int precision);
 /* 1 if (T, C) is supported by the given precision's kernels (forward AND training) on this build, else 0 */
 int b2h_supported(int T, int n_in, int C, int pos_emb, int precision);
@@ -116,6 +119,12 @@ int b2h_conv_forward(const void* x, int x_dtype, const float* params, const void
                      float* y, int B, int T, int n_in, int C, int pos_emb, int precision, int apply_mask,
                      float out_scale, void* stream);
 
+/* LinearPositionalEmbedding.forward as a stand-alone call (models/HandPoseModels.py:78-84): inp (B, channels, T) fp32
+ * -> out (B, channels+1, T) with out[:,0,t] = t / max_len (fp32 division) and the input channels behind it.  Like the
+ * reference's torch.cat it only works for T == max_len (B2H_ESHAPE otherwise).  ConvModel(pos_emb=True) does not
+ * call this: its kernels generate the row on the fly. */
+int b2h_pos_emb_concat(const float* inp, float* out, int B, int channels, int T, int max_len, void* stream);
+
 /* ---- K2 fused forward + loss + backward --------------------------------------------------------
  * One iteration of steps/traintest.py:94-120 up to loss.backward():  forward, mask_output,
  * maskedPoseL1 / poderatedPoseL1, and every parameter gradient (conv dgrad/wgrad/bias-grad, ReLU
@@ -156,10 +165,12 @@ int b2h_format_prediction(const float* pred, float* out, int64_t rows, int mode,
  * g = grads*grad_scale (grad_scale = 1/world for data parallel); m,v,p updated in place; when
  * `packed` is non-null the new weights are also scattered into the packed operand layouts so the
  * next forward needs no re-pack.  step is 1-based; step_dev (nullable) is a device int64 read
- * instead of `step` (CUDA-graph replay: the counter is advanced by the train kernel). */
+ * instead of `step` (CUDA-graph replay: the counter is advanced by the train kernel); lr_dev (nullable) is a device
+ * double read instead of `lr`, so a captured graph follows the reference's per-epoch learning-rate decay
+ * (adjust_learning_rate, steps/utils.py:301-307, called at steps/traintest.py:83-84) without a re-capture. */
 int b2h_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
-                  double beta1, double beta2, double eps, int64_t step, const int64_t* step_dev, float grad_scale,
-                  void* packed, int n_in, int C, int pos_emb, void* stream);
+                  double beta1, double beta2, double eps, int64_t step, const int64_t* step_dev, const double* lr_dev,
+                  float grad_scale, void* packed, int n_in, int C, int pos_emb, void* stream);
 
 /* ---- data parallel over peer (NVLink / NVSwitch) memory -----------------------------------------------------
  * The reference is single-process; training shards by batch with ONE gradient exchange per step.
@@ -176,31 +187,39 @@ int b2h_train_forward_backward_dp(const void* x, int x_dtype, const float* targe
                                   int64_t workspace_bytes, void* stream);
 int b2h_adam_step_dp(float* params, const void* peer_bufs_dev, int rank, int world, float* exp_avg, float* exp_avg_sq,
                      int64_t n, double lr, double beta1, double beta2, double eps, const int64_t* step_dev,
-                     const int64_t* epoch_dev, float grad_scale, void* packed, int n_in, int C, int pos_emb, void* stream);
+                     const int64_t* epoch_dev, const double* lr_dev, float grad_scale, void* packed, int n_in, int C,
+                     int pos_emb, void* stream);
 /* floats a rank's exchange buffer must hold for b2h_train_step_dp / b2h_adam_step_dp */
 int64_t b2h_dp_exchange_floats(int n_in, int C, int pos_emb, int world);
 
 /* The whole data-parallel step as ONE call; in bf16 mode (tensor-core tile kernel) also ONE cooperative kernel
- * launch per rank: forward + loss + backward, grid barrier, cross-CTA reduction into the exchange buffer, flag
- * exchange + gradient sum over peer memory, Adam + re-pack.  Other shapes run the same protocol as three launches. */
+ * launch per rank: forward + loss + backward, grid barrier, cross-CTA reduction, gradient exchange over peer memory
+ * (8-byte {value, epoch tag} words pushed into every rank's buffer), sum in rank order, Adam + re-pack.
+ * multicast_buf (nullable): the multicast (NVLS) address of the ranks' exchange buffers
+ * (torch symmetric-memory handle .multicast_ptr): the push is then ONE multimem.st per gradient slot, replicated by
+ * the NVSwitch, instead of `world` unicast stores.  lr_dev: see b2h_adam_step.  A wait for a peer that exceeds ~3 s
+ * sets the status read by b2h_tc_status / b2h_dp_status and suppresses every parameter update until it is read.
+ * Other shapes run the same protocol as three launches. */
 int b2h_train_step_dp(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,
                       float* params, void* packed, float* exp_avg, float* exp_avg_sq, float* loss_out, int B, int T,
                       int n_in, int C, int pos_emb, int loss_kind, int precision, double lr, double beta1, double beta2,
-                      double eps, int64_t* step_dev, int64_t* epoch_dev, float* sym_grads, const void* peer_bufs_dev,
-                      int rank, int world, float grad_scale, void* workspace, int64_t workspace_bytes, void* stream);
+                      double eps, int64_t* step_dev, int64_t* epoch_dev, const double* lr_dev, float* sym_grads,
+                      const void* peer_bufs_dev, void* multicast_buf, int rank, int world, float grad_scale, void* workspace,
+                      int64_t workspace_bytes, void* stream);
 /* 0 = clean, 1 = a peer-flag wait gave up (bounded spin); reading clears it.  Synchronises the device. */
 int b2h_dp_status(void);
 
 /* Fast path = b2h_train_forward_backward + b2h_adam_step with the cross-CTA gradient reduction
  * fused into the Adam kernel (2 launches per step, zero host work); in bf16 mode with step_dev the reduction and
  * Adam run in the tail of the SAME cooperative launch (1 launch per step; the workspace must be zero-initialised
- * once: it holds the grid-barrier words).  step_dev (nullable): a device
+ * once when it is allocated: its first 1024 bytes hold the launch sequence number and the per-CTA arrival flags of
+ * the in-kernel grid barrier, at a fixed offset whatever (B, T) is).  step_dev (nullable): a device
  * int64 holding the number of steps taken so far; when given it is incremented on the device and
  * used instead of `step`, so a captured CUDA graph of this call can be replayed step after step. */
 int b2h_train_step(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,
                    float* params, void* packed, float* exp_avg, float* exp_avg_sq, float* loss_out, int B, int T,
                    int n_in, int C, int pos_emb, int loss_kind, int precision, double lr, double beta1,
-                   double beta2, double eps, int64_t step, int64_t* step_dev, void* workspace,
+                   double beta2, double eps, int64_t step, int64_t* step_dev, const double* lr_dev, void* workspace,
                    int64_t workspace_bytes, void* stream);
 
 /* tcgen05 / TMEM / descriptor self-test (tests/test_tc_probe.py): D = A·B^T for one 128xNx(16*ksteps)

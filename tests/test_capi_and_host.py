@@ -56,6 +56,16 @@ def test_geometry_queries():
     assert lib.b2h_forward_supported(64, 24, 256, 0, _lib.FP32) == 1
 
 
+def test_gradient_partial_slot_layout_is_a_bijection():
+    """The tensor-core train kernel reads its weight-gradient accumulators out as [k][ci/4][co][4] slots (coalesced
+    stores); the Adam tail maps slots back to flat parameter indices.  Host-side check of that map for every geometry
+    the kernel serves (incl. pos_emb's 25 input channels and C = 32 where cin == the padded reduction)."""
+    lib = _lib.load()
+    for n_in, C, pe in ((24, 30, 0), (24, 30, 1), (24, 32, 0), (24, 16, 0), (16, 30, 0), (24, 64, 0), (24, 256, 0), (24, 1, 0)):
+        assert lib.b2h_gp_layout_check(n_in, C, pe) == 0, (n_in, C, pe)
+    assert lib.b2h_workspace_bytes(256, 64, 24, 30, 0, _lib.BF16) > 1024 + 128 * 19032 * 4
+
+
 def test_kernel_choice_pins_the_tensor_core_paths():
     """The dispatch of b2h_conv_forward / the train entry points goes through b2h_kernel_choice: in bf16 mode every
     BASELINE config, the reference default crop (200 frames) and the wide variant run tcgen05 kernels -- no silent
@@ -97,7 +107,7 @@ def test_null_and_bad_arguments_return_error_codes():
     assert lib.b2h_preprocess(None, None, None, 0, None, None, 0, 64, 0, 1280.0, 1, 1, None, None, None, None, None, None,
                               None, None, None) == -1
     assert lib.b2h_pack_weights(None, None, 24, 30, 0, None) == -1
-    assert lib.b2h_adam_step(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 1, None, 1.0, None, 0, 0, 0, None) == -1
+    assert lib.b2h_adam_step(None, None, None, None, 10, 1e-3, 0.9, 0.999, 1e-8, 1, None, None, 1.0, None, 0, 0, 0, None) == -1
 
 
 def test_convmodel_is_a_drop_in_on_the_host_side():

@@ -48,6 +48,8 @@ def _worker(rank, world, port, prec, kind, exchange, ret):
         torch.cuda.synchronize()
         from hand_pose_sl_b200 import _lib
         assert _lib.load().b2h_dp_status() == 0, "peer-flag wait timed out"
+        assert _lib.load().b2h_tc_status() == 0, "fused exchange: wait for a peer's gradient words timed out"
+        tr.check_status()
         if rank == 0:
             torch.manual_seed(0)
             ref = b2h.ConvModel(30, "ReLU", False, precision=prec).to(dev)
@@ -67,9 +69,12 @@ def _worker(rank, world, port, prec, kind, exchange, ret):
         ret[rank] = f"{type(e).__name__}: {e}\n{traceback.format_exc()}"
     finally:
         # destroy_process_group hangs while a captured graph still holds NCCL kernels: leave without the teardown
-        torch.cuda.synchronize()
+        try:
+            torch.cuda.synchronize()
+        except Exception:  # noqa: BLE001
+            pass
         sys.stdout.flush()
-        os._exit(0)
+        os._exit(0 if ret.get(rank) == "ok" else 1)
 
 
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
@@ -80,5 +85,8 @@ def test_data_parallel_matches_single_gpu(prec, kind, exchange):
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
     port = 29600 + (os.getpid() % 1000) + (7 if exchange == "p2p" else 0) + (len(prec) + len(kind)) * 11
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, port, prec, kind, exchange, ret), nprocs=world, join=True)
-    assert all(v == "ok" for v in ret.values()), dict(ret)
+    try:
+        mp.spawn(_worker, args=(world, port, prec, kind, exchange, ret), nprocs=world, join=True)
+    except Exception as e:  # noqa: BLE001  (a worker exited non-zero: its message is in `ret`)
+        assert False, (str(e)[:300], dict(ret))
+    assert len(ret) == world and all(v == "ok" for v in ret.values()), dict(ret)

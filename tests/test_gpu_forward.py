@@ -176,3 +176,16 @@ def test_inference_output_formats():
         assert np.array_equal(h5[b], oracle.order_and_reshape_toh5(yc[b]))
         for t_ in (0, 17, yc.shape[1] - 1):
             assert np.array_equal(op[b, t_], oracle.array2open_pose(yc[b, t_]))
+
+
+def test_linear_positional_embedding_forward_matches_reference_semantics():
+    """LinearPositionalEmbedding.forward(inp, lengths) (HandPoseModels.py:78-84): cat([t/100, inp], dim=1), bit-exact;
+    T != max_len raises like the reference's torch.cat."""
+    import hand_pose_sl_b200 as b2h
+    pe = b2h.LinearPositionalEmbedding(max_len=100)
+    inp = torch.randn(3, 24, 100, generator=torch.Generator().manual_seed(0))
+    want = torch.cat([torch.cat(3 * [(torch.arange(100)[None, None, :].float() / 100)], dim=0), inp], dim=1)
+    got = pe(inp.to("cuda:0"), None)
+    assert got.shape == (3, 25, 100) and torch.equal(got.cpu(), want)
+    with pytest.raises(RuntimeError):
+        pe(torch.zeros(2, 24, 64, device="cuda:0"), None)

@@ -284,3 +284,109 @@ def test_loss_and_gradients_odd_shapes_vs_oracle(B, T, C, kind, prec):
         assert oracle.rel_err(pred.cpu().numpy(), e_pred.numpy()) <= 2e-3
         for k, v in _split(m, grads).items():
             assert oracle.rel_err(v, e_g[k].numpy()) <= 1e-2, k
+
+
+def test_runners_of_different_shapes_share_one_workspace():
+    """the fused kernel's grid-barrier words sit in the workspace HEADER (fixed offset), so a small-batch
+    runner used after a large-batch one on the same model (remainder batch) never finds stale gradient partials where
+    it expects barrier state.  Large -> small -> large, losses must equal fresh single-runner results."""
+    from hand_pose_sl_b200.runner import TrainStepRunner
+    sd = oracle.init_params(30, False, seed=3)
+    big = synthetic.model_batch(256, 64, seed=11, ragged=True)
+    small = synthetic.model_batch(6, 64, seed=12, ragged=True)
+
+    def run(order):
+        m = _model(sd, 30, False, "bf16")
+        opt = b2h.FusedAdam(m.parameters(), lr=2e-4)
+        runners = {"big": TrainStepRunner(m, opt, 256, 64, "L1"), "small": TrainStepRunner(m, opt, 6, 64, "L1")}
+        assert runners["big"].ws.data_ptr() == runners["small"].ws.data_ptr()      # one shared per-model workspace
+        runners["big"].load(big, non_blocking=False); runners["small"].load(small, non_blocking=False)
+        out = [float(runners[k].step(0)) for k in order]
+        torch.cuda.synchronize()
+        assert _lib.load().b2h_tc_status() == 0
+        return out, m.flat_parameters().clone()
+
+    l1, w1 = run(["big", "small", "big", "small"])
+    l2, w2 = run(["big", "small", "big", "small"])
+    assert l1 == l2 and torch.equal(w1, w2)                                         # deterministic, no stale state
+    # each step's loss equals the oracle's on the same trajectory
+    st = oracle.TrainState(sd, lr=2e-4)
+    for i, k in enumerate(["big", "small", "big", "small"]):
+        b = big if k == "big" else small
+        ref_loss, _ = oracle.train_step(st, b["input_kp"], b["target_kp"], b["n_frames"])
+        assert abs(l1[i] - ref_loss) <= TOL["bf16"] * abs(ref_loss), (i, l1, ref_loss)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_captured_graph_follows_learning_rate_changes(prec):
+    """the learning rate lives in device memory, so adjust_learning_rate (traintest.py:83-84) takes effect
+    on a captured graph without a re-capture: graph steps with a mid-way lr change == eager steps with the same change."""
+    from hand_pose_sl_b200.runner import TrainStepRunner
+    g = load_golden("convmodel_c30.npz")
+    sd = golden_sd(g)
+    batch = {"input_kp": torch.from_numpy(g["input_kp"]), "target_kp": torch.from_numpy(g["target_kp"]),
+             "n_frames": torch.from_numpy(g["lengths"])}
+    B, T = g["input_kp"].shape[:2]
+    results = []
+    for graph in (False, True):
+        m = _model(sd, 30, False, prec)
+        opt = b2h.FusedAdam(m.parameters(), lr=1e-3)
+        r = TrainStepRunner(m, opt, B, T, "L1")
+        r.load(batch, non_blocking=False)
+        if graph:
+            r.capture(1)
+        for s in range(4):
+            if s == 2:
+                b2h.adjust_learning_rate(1e-3, 1, opt, 2)          # lr = 1e-5 from step 3 on
+            r.replay() if graph else r.step(0)
+        r.finish()
+        results.append(m.flat_parameters().clone())
+    assert torch.equal(results[0], results[1])
+    # and the change really took effect: two more steps at lr=1e-3 would have moved the weights further
+    m = _model(sd, 30, False, prec)
+    opt = b2h.FusedAdam(m.parameters(), lr=1e-3)
+    r = TrainStepRunner(m, opt, B, T, "L1")
+    r.load(batch, non_blocking=False)
+    for s in range(4):
+        r.step(0)
+    assert not torch.equal(m.flat_parameters(), results[0])
+
+
+def test_forward_runner_follows_weight_changes():
+    """ForwardRunner re-packs when the parameters' version counters moved (load_state_dict after
+    construction), also for a captured graph (the packed buffer keeps its address)."""
+    from hand_pose_sl_b200.runner import ForwardRunner
+    sd_a, sd_b = oracle.init_params(30, False, seed=1), oracle.init_params(30, False, seed=2)
+    batch = synthetic.model_batch(4, 64, seed=5)
+    m = _model(sd_a, 30, False, "bf16")
+    fr = ForwardRunner(m, 4, 64)
+    fr.x[0].copy_(batch["input_kp"])
+    ya = fr.run(0).clone()
+    fr.capture(1)
+    m.load_state_dict(sd_b)
+    yb_graph = None
+    fr.replay(); yb_graph = fr.y[0].clone()
+    yb = fr.run(0).clone()
+    ref_b = oracle.conv_model_forward(sd_b, batch["input_kp"]).contiguous().numpy()
+    assert oracle.rel_err(yb.cpu().numpy(), ref_b) <= TOL["bf16"] and torch.equal(yb, yb_graph)
+    assert not torch.equal(ya, yb)
+
+
+def test_staged_single_copy_inputs_are_bit_identical():
+    """runner.host_stage + load_staged (ONE H2D copy, bf16 keypoint input) == load(batch) with fp32 inputs in bf16 mode."""
+    from hand_pose_sl_b200.runner import TrainStepRunner
+    sd = oracle.init_params(30, False, seed=4)
+    batch = synthetic.model_batch(32, 64, seed=21, ragged=True)
+    out = []
+    for staged in (False, True):
+        m = _model(sd, 30, False, "bf16")
+        opt = b2h.FusedAdam(m.parameters(), lr=2e-4)
+        r = TrainStepRunner(m, opt, 32, 64, "confL1", n_slots=2, x_dtype=torch.bfloat16 if staged else None)
+        if staged:
+            r.load_staged(r.host_stage(batch), slot=1, non_blocking=False)
+        else:
+            r.load(batch, slot=1, non_blocking=False)
+        losses = [float(r.step(1)) for _ in range(3)]
+        r.finish()
+        out.append((losses, m.flat_parameters().clone()))
+    assert out[0][0] == out[1][0] and torch.equal(out[0][1], out[1][1])
