@@ -30,6 +30,7 @@
 // copies (prefetched at tile start), the prediction tile by bulk stores; inputs are prefetched into registers
 // one tile ahead (fp32 -> bf16 conversion happens on the way to shared memory).
 #pragma once
+#include <type_traits>
 
 namespace b2h {
 using namespace tc;
@@ -55,6 +56,7 @@ constexpr int kTileThreads = 256;   // 8 warps: two per TMEM lane quadrant (each
 constexpr int kAccCol = 0;        // forward / dgrad accumulator: columns [0, 64)
 // weight-gradient accumulators follow the forward/dgrad accumulators: 2 layer pairs x (5 taps x 32 + 8 bias) columns
 constexpr int kWgPairCols = 5 * 32 + 8;
+constexpr int kGatherDepth = 24; // independent 16-B loads in flight per thread in the cross-CTA gradient gather
 constexpr int kDpMaxCta = 160;    // flag slots per rank in the data-parallel exchange buffer (>= CTAs of the train kernel)
 
 struct TileSmem {   // byte offsets into dynamic smem
@@ -492,6 +494,46 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         if (tgt_smem && j == 0) { mbar_wait(&tbar, tphase, 18); tphase ^= 1; }
         B2H_STAMP();   // layer-4 epilogue: target tile landed
         float sum = 0.f;
+        // Fast path of the headline configuration (maskedPoseL1 inside, target tile staged in shared memory, prediction
+        // not requested): the chunk's first column is a compile-time constant, so every `column < 42` test folds away
+        // and the body is straight-line code -- the generic loop below executed ~4x the instructions of a hidden
+        // layer's epilogue (per-element predicates for the confidence weights, the given-d_y mode and the y store).
+        const bool l4_fast = TRAIN && p.mode == 1 && p.loss_kind == B2H_LOSS_L1 && tgt_smem && p.y == nullptr;
+        if (TRAIN && l4_fast) {
+          const bool live = valid && (t < len);          // rows t >= len are zeroed by mask_output and carry no loss
+          auto chunk = [&](auto c0_tag) {
+            constexpr int C0 = decltype(c0_tag)::value;
+            uint32_t v[16];
+            tmem_ld16(taddr + C0, v);
+            float tv[16];
+            const float2* tp = reinterpret_cast<const float2*>(ys_row + C0);
+#pragma unroll
+            for (int q2 = 0; q2 < 8; ++q2) {
+              if (C0 + 2 * q2 < B2H_COUT) { const float2 t2 = tp[q2]; tv[2 * q2] = t2.x; tv[2 * q2 + 1] = t2.y; }
+              else { tv[2 * q2] = 0.f; tv[2 * q2 + 1] = 0.f; }
+            }
+            tmem_ld_wait();
+            float gq[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              if (C0 + q < B2H_COUT) {
+                const float a = live ? __uint_as_float(v[q]) + bias_s[3][C0 + q] : 0.0f;      // masked prediction
+                const float d = __fsub_rn(a, tv[q]);        // == a*1 - t*1 of the weighted form, exactly
+                sum += live ? fabsf(d) : 0.0f;
+                const float gr = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+                gq[q] = live ? gr : 0.0f;
+              } else {
+                gq[q] = 0.0f;
+              }
+            }
+            store8_bf16(G0, CH, row, C0 >> 3, gq);
+            store8_bf16(G0, CH, row, (C0 >> 3) + 1, gq + 8);
+          };
+          if (ch == 0) { chunk(std::integral_constant<int, 0>{}); chunk(std::integral_constant<int, 32>{}); }
+          else chunk(std::integral_constant<int, 16>{});
+          B2H_STAMP();   // layer-4 epilogue: chunks done (fast path)
+          B2H_STAMP();
+        } else
         for (int c0 = 16 * ch; c0 < N; c0 += 32) {
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
@@ -686,9 +728,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       // ---- work that does not need the other CTAs, done while the slowest CTA is still on its way to the barrier:
       // bias corrections (double-precision powers), decode of this thread's slot, its Adam state (m, v, p) ----
       if (tid == kTileThreads - 1) {                     // last thread: usually idle in the gather below
-        const double lr = f.lr_dev ? *f.lr_dev : f.lr;
-        s_step_size = (float)(lr / (1.0 - ipow(f.beta1, step_next)));
-        s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - ipow(f.beta2, step_next)));
+        // bias corrections 1 - beta^t = -expm1(t * log1p(beta - 1)) in fp32 (relative error ~3e-7 for every t, also
+        // where 1 - beta^t cancels): the double-precision powers of round 1 cost ~5k cycles on B200's few FP64 units
+        const float lr = (float)(f.lr_dev ? *f.lr_dev : f.lr);
+        const float tt = (float)step_next;
+        const float bc1 = -expm1f(tt * log1pf((float)(f.beta1 - 1.0)));
+        const float bc2 = -expm1f(tt * log1pf((float)(f.beta2 - 1.0)));
+        s_step_size = lr / bc1;
+        s_inv_bc2_sqrt = 1.0f / sqrtf(bc2);
       }
       const bool one_pass = per <= kTileThreads;         // the usual case: one slot per thread
       GpSlot my_slot;
@@ -732,15 +779,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
             const float4* src = reinterpret_cast<const float4*>(p.partials + jb + 4 * col);
             const size_t stride4 = (size_t)nj >> 2;
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int c = pg; c < nparts; c += 16 * groups) {
-              float4 v[16];
+            for (int c = pg; c < nparts; c += kGatherDepth * groups) {
+              float4 v[kGatherDepth];                     // 128 slices / 6 groups = 22 loads: one batch in flight
 #pragma unroll
-              for (int u = 0; u < 16; ++u) {
+              for (int u = 0; u < kGatherDepth; ++u) {
                 const int cc = c + u * groups;
                 v[u] = (cc < nparts) ? __ldcg(src + (size_t)cc * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
               }
 #pragma unroll
-              for (int u = 0; u < 16; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+              for (int u = 0; u < kGatherDepth; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
             }
             red4[pg * ncol + col] = acc;
           }
@@ -865,7 +912,11 @@ int launch_tc_tile(TcTileArgs& p, bool train, cudaStream_t stream) {
   if (int rc = ensure_dyn_smem(fn, smem)) return rc;
   void* kargs[] = {&p};
   cudaError_t le;
-  if (train && p.fuse.enabled)   // grid barriers inside: cooperative launch guarantees that all CTAs (<= 1 per SM) are co-resident
+  // Grid barrier inside: a cooperative launch guarantees that all CTAs (<= 1 per SM) are co-resident.  B2H_NONCOOP=1
+  // (measurement aid, read once) uses a plain launch of the same grid: identical residency on an otherwise idle GPU,
+  // but nothing guarantees it when other kernels share the device.
+  static const bool noncoop = [] { const char* e = getenv("B2H_NONCOOP"); return e && e[0] == '1'; }();
+  if (train && p.fuse.enabled && !noncoop)
     le = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kTileThreads), kargs, smem, stream);
   else
     le = cudaLaunchKernel(fn, dim3(grid), dim3(kTileThreads), kargs, smem, stream);
