@@ -412,7 +412,7 @@ extern "C" int b2h_tc_bench(void* out_i64x2, int M, int N, int reps, int nacc, i
   return launch_tc_bench(reinterpret_cast<long long*>(out_i64x2), M, N, reps, nacc, mn_major, (cudaStream_t)stream);
 }
 
-extern "C" void b2h_debug_timing(void* dev_i64x128) { set_debug_timing(reinterpret_cast<long long*>(dev_i64x128)); }
+extern "C" void b2h_debug_timing(void* dev_i64x1024) { set_debug_timing(reinterpret_cast<long long*>(dev_i64x1024)); }
 
 extern "C" int b2h_tc_status(void) { return tc_status_and_clear(); }
 

@@ -162,6 +162,10 @@ __device__ __forceinline__ void adam_apply(const FuseAdam& f, const Geo& g, cons
 }
 
 #define B2H_STAMP() do { if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 120) p.dbg[dbg_n++] = clock64(); } while (0)
+// per-CTA wall-clock marks (ns, %globaltimer is common to all SMs): dbg[128 + 4 * cta + i], i = 0 start, 1 arrival at the
+// grid barrier, 2 barrier passed, 3 end -- shows how much of a barrier wait is CTA launch skew
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define B2H_MARK(i) do { if (p.dbg && tid == 0 && blockIdx.x < 192) p.dbg[128 + 4 * blockIdx.x + (i)] = global_ns(); } while (0)
 
 // NT (128-row MMA tiles per segment) is a compile-time constant: with it at run time the per-row loops and the row
 // context inside them cost the T <= 128 shapes ~6 % (27.4 -> 29.1 us per train step, 10.5 -> 11.3 us forward).
@@ -192,6 +196,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   unsigned char* ONES = smem + L.ones;
   float* YS = reinterpret_cast<float*>(smem + L.ys);
   B2H_STAMP();   // kernel start
+  if (TRAIN) B2H_MARK(0);
 
   // this thread's row: TMEM lane == tid & 127 (warps w and w+4 share lane quadrant w & 3 and split the columns)
   const int r128 = tid & 127;
@@ -745,8 +750,11 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         my_i = gp_flat_of_slot(g, my_slot);
         my_m = __ldcg(f.m + my_i); my_v = __ldcg(f.v + my_i); my_p = __ldcg(f.params + my_i);
       }
+      B2H_MARK(1);
+      bool aborted = dp && (*reinterpret_cast<volatile int*>(&g_dp_abort) != 0);   // set by an earlier step's peer timeout
       grid_barrier_flags(f.hdr, sync_tok, tid);          // every CTA's partial slice is visible
       B2H_STAMP();   // tail: grid barrier passed
+      B2H_MARK(2);
       if (blockIdx.x == 0 && tid == 0) {                 // publish the counters for the next launch
         *reinterpret_cast<volatile unsigned*>(f.hdr) = sync_tok;
         *p.step_dev = step_next;
@@ -817,31 +825,36 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
                 reinterpret_cast<const volatile unsigned long long*>(f.peer_bufs[f.rank]) + (size_t)(epoch & 1) * f.world * nj + j;
             const long long t0 = clock64();
             for (int rb = 0; rb < f.world; rb += 8) {
-              // up to 8 ranks' words are requested before the first one is examined: one L2 round trip for the group
+              // All (<= 8) ranks' words are requested together and the whole group is re-read until every tag matches:
+              // one L2 round trip per polling round.  (Round 1 re-polled the missing words one after the other -- at 8
+              // ranks the first read comes back stale for almost everyone, which cost one round trip PER RANK.)
               unsigned long long w[8];
+              bool all_here;
+              do {
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (rb + u < f.world) w[u] = mine[(size_t)(rb + u) * nj];
+                all_here = true;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                  if (rb + u < f.world) all_here = all_here && ((uint32_t)(w[u] >> 32) == tag);
+                if (!all_here && clock64() - t0 > 6000000000LL) {        // ~3 s: a peer never arrived
+                  atomicExch(&g_tc_status, 51);
+                  atomicExch(&g_dp_abort, 1);
+                  aborted = true;
+                  break;
+                }
+              } while (!all_here);
 #pragma unroll
               for (int u = 0; u < 8; ++u)
-                if (rb + u < f.world) w[u] = mine[(size_t)(rb + u) * nj];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                if (rb + u < f.world) {
-                  while ((uint32_t)(w[u] >> 32) != tag) {
-                    if (clock64() - t0 > 6000000000LL) {        // ~3 s: a peer never arrived
-                      atomicExch(&g_tc_status, 51);
-                      atomicExch(&g_dp_abort, 1);
-                      break;
-                    }
-                    w[u] = mine[(size_t)(rb + u) * nj];
-                  }
-                  gsum += __uint_as_float((uint32_t)w[u]);       // rank order: identical arithmetic on every rank
-                }
-              }
+                if (rb + u < f.world) gsum += __uint_as_float((uint32_t)w[u]);       // rank order: identical arithmetic on every rank
             }
             B2H_STAMP();   // tail: world's slots collected
             gr = gsum;
-            // Sticky abort: after a peer timeout NO parameter / moment is written (this step and every later one, until
-            // the host has read and cleared the status) -- replicas may stall, they never silently diverge.
-            apply = *reinterpret_cast<volatile int*>(&g_dp_abort) == 0;
+            // Sticky abort: after a peer timeout no parameter / moment is written by the threads that missed a word, nor
+            // by anybody in any later step, until the host has read and cleared the status (the flag of earlier steps
+            // was fetched before the grid barrier) -- replicas may stall, the failure is never silent.
+            apply = !aborted;
           }
           if (apply) {
             if (one_pass) {
@@ -858,6 +871,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         __syncthreads();
       }
       B2H_STAMP();   // tail: reduction (+ exchange) + Adam done
+      B2H_MARK(3);
     }
   }
   if (!TRAIN && tid == 0) bulk_wait0();

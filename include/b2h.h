@@ -242,9 +242,11 @@ int b2h_tc_status(void);
  *   reps = rounds, nacc = ring depth in 8-KB stages (<= 16), mn_major = CTAs; out[0] = cycles, out[1] = bytes. */
 int b2h_tc_bench(void* out_i64x2, int M, int N, int reps, int nacc, int mn_major, void* stream);
 
-/* Bring-up aid: when set to a device buffer of 128 int64, CTA 0 of the tile kernels stamps clock64() at every
- * phase boundary (setup, staging, per-layer issue / ready / epilogue); NULL switches it off. */
-void b2h_debug_timing(void* dev_i64x128);
+/* Bring-up aid: when set to a device buffer of 1024 int64, CTA 0 of the tile kernels stamps clock64() at every
+ * phase boundary (setup, staging, per-layer issue / ready / epilogue) into words [0, 128), and every CTA c of the fused
+ * train kernel writes %globaltimer (ns) at its start / barrier arrival / barrier exit / end into words
+ * [128 + 4c, 128 + 4c + 4); NULL switches it off. */
+void b2h_debug_timing(void* dev_i64x1024);
 
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t b2h_launch_count(void);

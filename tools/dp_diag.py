@@ -43,7 +43,7 @@ if os.environ.get("B2H_DIAG_GRAPH", "1") == "1":
     torch.cuda.synchronize(); say("graph steps", (time.time() - t0) / 100 * 1e6, "us/step")
 from hand_pose_sl_b200 import _lib
 lib = _lib.load()
-buf = torch.zeros(128, dtype=torch.int64, device=dev)
+buf = torch.zeros(1024, dtype=torch.int64, device=dev)
 for rep in range(2):
     torch.cuda.synchronize(); dist.barrier()
     buf.zero_(); lib.b2h_debug_timing(_lib.ptr(buf))

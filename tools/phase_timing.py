@@ -20,7 +20,7 @@ if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=dev)
 lib = _lib.load()
-buf = torch.zeros(128, dtype=torch.int64, device=dev)
+buf = torch.zeros(1024, dtype=torch.int64, device=dev)
 
 FWD = (["start", "setup", "staging", "weights"] + [f"F{l}:{p}" for l in range(3) for p in ("issued", "ready", "epilogue")]
        + ["F3:issued", "F3:ready", "F3:target", "F3:chunk0", "F3:chunk1", "F3:epilogue"])
@@ -32,8 +32,25 @@ TAIL1 = ["adam", "end"]
 TAILDP = ["pushed", "collected", "adam", "end"]
 
 
+def marks(name):
+    """per-CTA %globaltimer marks of the fused train kernel: launch skew vs barrier wait"""
+    m = buf.cpu()[128:128 + 4 * 192].view(192, 4)
+    m = m[m[:, 0] != 0]
+    if m.numel() == 0:
+        return
+    t0 = int(m[:, 0].min())
+    start, arrive, passed, end = [(m[:, i] - t0).tolist() for i in range(4)]
+    srt = sorted(start)
+    print(f"[r{rank}] {name}: {len(start)} CTAs; start spread {max(start)} ns (median {srt[len(srt) // 2]}), "
+          f"arrive min/median/max {min(arrive)}/{sorted(arrive)[len(arrive) // 2]}/{max(arrive)} ns, "
+          f"pass min/max {min(passed)}/{max(passed)}, end min/max {min(end)}/{max(end)}; "
+          f"own work (arrive-start) min/median/max {min(a - b for a, b in zip(arrive, start))}/"
+          f"{sorted(a - b for a, b in zip(arrive, start))[len(start) // 2]}/{max(a - b for a, b in zip(arrive, start))}", flush=True)
+
+
 def show(name, labels):
-    st = [int(v) for v in buf.cpu().tolist() if v != 0]
+    marks(name)
+    st = [int(v) for v in buf.cpu()[:128].tolist() if v != 0]
     d = [st[i + 1] - st[i] for i in range(len(st) - 1)]
     lab = labels[1:len(st)] + ["?"] * max(0, len(st) - len(labels))
     print(f"[r{rank}] {name}: {len(st)} stamps, total {st[-1] - st[0]} cycles")
