@@ -564,14 +564,39 @@ def main():
                                                "note": "CUDA-graph replay, outputs reused; 314 MB moved per launch > 126 MB L2"}}
         if not args.skip_extras:
             # ---------------- config 5: streaming K0 -> K1 over 1 h of frames (stride 64 and 16) ----------------
+            # K0 runs ONCE per unique frame and writes only what the net reads (a (F,12,2) bf16 stream); the forward reads
+            # the sliding windows as views of that stream (crop + pad rule on the fly): overlapping windows are never
+            # materialised.  "materialised" = the round-1 pipeline (K0 writes every window's full item) for comparison.
             Fs = 108000
             sp_, sl_, sr_ = (t_[:Fs].contiguous() for t_ in (tp, tl, tr))
-            pre_s = b2h.PreprocessRightHand(with_left_hand=False, emit_bf16=(fwd_prec == "bf16"))
-            line["stream"] = {"workload": f"{Fs} frames (1 h at 30 fps): K0 preprocessing (+bf16 copy) -> forward over 64-frame windows, CUDA graph",
-                              "dtype": fwd_prec}
+            line["stream"] = {"workload": f"{Fs} frames (1 h at 30 fps): K0 per unique frame -> bf16 frame stream -> forward over "
+                                          f"64-frame window views (x1280 de-normalise fused), CUDA graph", "dtype": fwd_prec}
             for stride in (64, 16):
-                st_ = torch.from_numpy(b2h.sliding_window_starts(Fs - T + 1, T, stride)).to(dev)
+                st_np = b2h.sliding_window_starts(Fs - T + 1, T, stride)
+                st_ = torch.from_numpy(st_np).to(dev)
                 Wn = st_.numel()
+                entry = {"windows": Wn}
+                if fwd_prec == "bf16":
+                    pre_v = b2h.PreprocessRightHand()
+                    stream_buf = pre_v.frame_stream(sp_, sl_, sr_)
+                    yv = fmodel.predict_windows(stream_buf, st_, T, denormalize=1280.0)
+                    torch.cuda.synchronize()
+                    sg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(sg):
+                        for _ in range(4):
+                            pre_v.frame_stream(sp_, sl_, sr_, out=stream_buf)
+                            fmodel.predict_windows(stream_buf, st_, T, denormalize=1280.0, out=yv)
+                    sg.replay(); torch.cuda.synchronize()
+                    ev0.record()
+                    for _ in range(5):
+                        sg.replay()
+                    ev1.record()
+                    torch.cuda.synchronize()
+                    s_ms = ev0.elapsed_time(ev1) / 20
+                    entry.update({"ms": s_ms, "unique_frames_per_sec": Fs / (s_ms * 1e-3), "window_frames_per_sec": Wn * T / (s_ms * 1e-3),
+                                  "path": "window views of the per-frame stream (no re-materialisation)"})
+                    del sg
+                pre_s = b2h.PreprocessRightHand(with_left_hand=False, emit_bf16=(fwd_prec == "bf16"))
                 so = pre_s(sp_, sl_, sr_, st_, T)
                 xin = so["input_kp_bf16"] if fwd_prec == "bf16" else so["input_kp"]
                 frs = ForwardRunner(fmodel, Wn, T, n_slots=1, x_dtype=xin.dtype, out_scale=1280.0)
@@ -589,9 +614,13 @@ def main():
                     sg.replay()
                 ev1.record()
                 torch.cuda.synchronize()
-                s_ms = ev0.elapsed_time(ev1) / 20
-                line["stream"][f"stride{stride}"] = {"windows": Wn, "ms": s_ms, "unique_frames_per_sec": Fs / (s_ms * 1e-3),
-                                                     "window_frames_per_sec": Wn * T / (s_ms * 1e-3)}
+                m_ms = ev0.elapsed_time(ev1) / 20
+                entry["materialised"] = {"ms": m_ms, "unique_frames_per_sec": Fs / (m_ms * 1e-3)}
+                if "ms" not in entry:
+                    entry.update({"ms": m_ms, "unique_frames_per_sec": Fs / (m_ms * 1e-3), "window_frames_per_sec": Wn * T / (m_ms * 1e-3),
+                                  "path": "materialised windows"})
+                line["stream"][f"stride{stride}"] = entry
+                del sg, frs, so
         # ---------------- CPU baseline (reference path on this box's host cores) ----------------
         line["cpu_baseline"], _, _ = cpu_reference_arm(200, 2, budget_s=15.0)
         if not args.skip_extras:

@@ -176,6 +176,32 @@ extern "C" int b2h_conv_forward(const void* x, int x_dtype, const float* params,
   return B2H_EINVAL;
 }
 
+extern "C" int b2h_conv_forward_windows(const void* frames, int x_dtype, int64_t n_frames, const int64_t* win_start,
+                                        const int64_t* win_end, int pad_mode, const float* params, const void* packed,
+                                        const int32_t* lengths, float* y, int n_win, int T, int n_in, int C, int pos_emb,
+                                        int precision, int apply_mask, float out_scale, void* stream) {
+  if (!frames || !win_start || !params || !packed || !y) { set_error("b2h_conv_forward_windows: null pointer"); return B2H_EINVAL; }
+  if (x_dtype != B2H_DT_F32 && x_dtype != B2H_DT_BF16) { set_error("b2h_conv_forward_windows: bad x_dtype %d", x_dtype); return B2H_EINVAL; }
+  if (pad_mode != B2H_PAD_REPEAT_FIRST && pad_mode != B2H_PAD_ZEROS) { set_error("b2h_conv_forward_windows: bad pad_mode %d", pad_mode); return B2H_EINVAL; }
+  if (!geo_ok(n_in, C, pos_emb, "b2h_conv_forward_windows")) return B2H_ESHAPE;
+  if (n_win < 0 || T < 1 || n_frames < 0) { set_error("b2h_conv_forward_windows: bad n_win=%d T=%d", n_win, T); return B2H_ESHAPE; }
+  if (apply_mask && !lengths) { set_error("b2h_conv_forward_windows: apply_mask needs lengths"); return B2H_EINVAL; }
+  if (n_win == 0) return B2H_OK;
+  if ((reinterpret_cast<uintptr_t>(frames) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(packed) & 15)) {
+    set_error("b2h_conv_forward_windows: frames, y and packed must be 16-byte aligned");
+    return B2H_EALIGN;
+  }
+  Geo g = make_geo(n_in, C, pos_emb);
+  if (precision != B2H_BF16 || forward_choice(g, T, precision) != B2H_KERNEL_TC_TILE) {
+    set_error("b2h_conv_forward_windows: window views are served by the tcgen05 tile kernel (bf16 mode, conv_channels <= 64, "
+              "T <= 256); materialise the windows (b2h_preprocess) for C=%d, T=%d, precision=%d", C, T, precision);
+    return B2H_ESHAPE;
+  }
+  WindowView wv{reinterpret_cast<const long long*>(win_start), reinterpret_cast<const long long*>(win_end), (long long)n_frames, pad_mode};
+  return launch_tc_tile_fwd(frames, x_dtype, params, reinterpret_cast<const char*>(packed), lengths, y, n_win, T, apply_mask, out_scale, g,
+                            (cudaStream_t)stream, &wv);
+}
+
 static int train_common(const void* x, int x_dtype, const float* target, const float* conf, const float* d_y,
                         const int32_t* lengths, const float* params, const void* packed, float* pred_out, int B, int T,
                         int n_in, int C, int pos_emb, int loss_kind, int precision, int mode, void* workspace,

@@ -253,8 +253,9 @@ int tc_status_and_clear();
 struct TcTileArgs;
 int tc_train_grid(const Geo& g, int B, int T);
 bool tc_tile_ok(const Geo& g, int T, bool train);
+struct WindowView { const long long* win_start; const long long* win_end; long long n_frames; int pad_mode; };
 int launch_tc_tile_fwd(const void* x, int x_dtype, const float* params, const char* packed, const int32_t* lengths, float* y,
-                       int B, int T, int apply_mask, float out_scale, const Geo& g, cudaStream_t stream);
+                       int B, int T, int apply_mask, float out_scale, const Geo& g, cudaStream_t stream, const WindowView* wv = nullptr);
 int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream);
 
 void set_debug_timing(long long* p);

@@ -66,6 +66,21 @@ struct PreArgs {
   __nv_bfloat16* input_bf16;
 };
 
+// Exact division by the normalisation factor without the generic div.rn sequence (whose special-operand
+// slow path is taken for every zero = undetected keypoint).  With rc = RN(1/c):  q = RN(x*rc),
+// r = x - q*c (exact, FMA), q' = RN(q + r*rc) is the correctly rounded x/c (Markstein) as long as nothing
+// over/underflows; outside that range the IEEE routine is used.  tests/test_gpu_preprocess.py checks the
+// identity for c = 1280 over ALL 2^32 float bit patterns on the device (b2h_verify_fastdiv).
+__device__ __forceinline__ float div_exact(float x, float c, float rc) {
+  const float ax = fabsf(x);
+  const float q = __fmul_rn(x, rc);
+  const float r = __fmaf_rn(-q, c, x);
+  float res = __fmaf_rn(r, rc, q);
+  res = (ax == 0.0f) ? x : res;             // (+-0)/c = +-0 for the positive factor (the FMA chain would lose -0)
+  if (!(ax < 1e30f) || (ax != 0.0f && !(ax > 1e-30f))) res = __fdiv_rn(x, c);   // never taken on keypoint data
+  return res;
+}
+
 template <int FMT>
 __device__ __forceinline__ float out_elem(const float* st, int a, int i, int r, const PreArgs& p) {
   using F = Fmt<FMT>;
@@ -75,7 +90,7 @@ __device__ __forceinline__ float out_elem(const float* st, int a, int i, int r, 
       int j = r >> 1, d = r & 1;
       v = F::body(st, i, j, d);
       if (p.dif) v = __fsub_rn(v, F::body(st, i, 1, d));
-      if (p.normalize) v = __fdiv_rn(v, p.factor);
+      if (p.normalize) v = p.fastdiv ? div_exact(v, p.factor, p.rfactor) : __fdiv_rn(v, p.factor);
       return v;
     }
     case 1: return F::body(st, i, r, 2);  // input_conf     utils.py:268
@@ -95,21 +110,6 @@ __device__ __forceinline__ float out_elem(const float* st, int a, int i, int r, 
     }
     default: return F::lh(st, i, r, 2);
   }
-}
-
-// Exact division by the normalisation factor without the generic div.rn sequence (whose special-operand
-// slow path is taken for every zero = undetected keypoint).  With rc = RN(1/c):  q = RN(x*rc),
-// r = x - q*c (exact, FMA), q' = RN(q + r*rc) is the correctly rounded x/c (Markstein) as long as nothing
-// over/underflows; outside that range the IEEE routine is used.  tests/test_gpu_preprocess.py checks the
-// identity for c = 1280 over ALL 2^32 float bit patterns on the device (b2h_verify_fastdiv).
-__device__ __forceinline__ float div_exact(float x, float c, float rc) {
-  const float ax = fabsf(x);
-  const float q = __fmul_rn(x, rc);
-  const float r = __fmaf_rn(-q, c, x);
-  float res = __fmaf_rn(r, rc, q);
-  res = (ax == 0.0f) ? x : res;             // (+-0)/c = +-0 for the positive factor (the FMA chain would lose -0)
-  if (!(ax < 1e30f) || (ax != 0.0f && !(ax > 1e-30f))) res = __fdiv_rn(x, c);   // never taken on keypoint data
-  return res;
 }
 
 __global__ void verify_fastdiv_kernel(float c, float rc, unsigned long long* mismatches) {
@@ -384,8 +384,9 @@ extern "C" int b2h_preprocess(const float* pose25, const float* hand_left, const
                               int dif_encoding, int normalize, float* input_kp, float* input_conf,
                               float* target_kp, float* target_conf, float* left_kp, float* left_conf,
                               int64_t* n_frames_out, void* input_kp_bf16, void* stream) {
-  if (!pose25 || !hand_left || !hand_right || !win_start || !input_kp || !input_conf || !target_kp || !target_conf) {
-    set_error("b2h_preprocess: null pointer");
+  if (!pose25 || !hand_left || !hand_right || !win_start) { set_error("b2h_preprocess: null pointer"); return B2H_EINVAL; }
+  if (!input_kp && !input_conf && !target_kp && !target_conf && !left_kp && !left_conf && !input_kp_bf16) {
+    set_error("b2h_preprocess: no output requested");
     return B2H_EINVAL;
   }
   if (pad_mode != B2H_PAD_REPEAT_FIRST && pad_mode != B2H_PAD_ZEROS) { set_error("b2h_preprocess: bad pad_mode %d", pad_mode); return B2H_EINVAL; }

@@ -46,6 +46,10 @@ struct TcTileArgs {
   long long* epoch_dev;
   long long* dbg;         // nullable: CTA 0 / thread 0 writes clock64() phase stamps here (b2h_debug_timing)
   FuseAdam fuse;
+  // Streaming inference (BASELINE config 5): when win_start is set, x is a per-frame stream (n_frames, n_in) and window
+  // w, frame t reads row win_start[w] + t of it (cut at win_end[w] / n_frames, then the dataset's pad rule) -- overlapping
+  // windows are views of the stream, nothing is re-materialised.
+  const long long* win_start; const long long* win_end; long long n_frames; int pad_mode;
   int B, T, loss_kind, apply_mask, mode;   // mode 0 = forward only, 1 = train (loss inside), 2 = backward of given d_y
   float out_scale;
   int n_tiles, nhalf, MB, HR, gh, NT;      // tile geometry (NT = 128-row MMA tiles per segment: 2 for 128 < T <= 256)
@@ -229,24 +233,39 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   const uint32_t seg_d = (nhalf == 2) ? (16u << 16) : 64u;
   const int cpr = n_in >> 3;
 
+  // source row of (window gw, frame tt) in p.x; -1 = a zero row.  Dense batches: gw*T + tt.  Window views of a frame
+  // stream: crop [start, start+T) cut at the clip end, then the pad rule (repeat the crop's first frame:
+  // text_pose_dataset.py:511-518; zeros: :614-622) -- the same integer work as K0's windowing, bit-exact.
+  auto xrow_of = [&](int gw, int tt) -> long long {
+    if (!p.win_start) return (long long)gw * T + tt;
+    const long long start = p.win_start[gw];
+    long long cend = p.win_end ? p.win_end[gw] : p.n_frames;
+    cend = cend > p.n_frames ? p.n_frames : cend;
+    long long f = start + tt;
+    if (f >= cend || f < 0) f = (p.pad_mode == B2H_PAD_REPEAT_FIRST && start >= 0 && start < cend) ? start : -1;
+    return f;
+  };
   // ---- input prefetch registers (one tile ahead) ----
   float4 xf[8];
   uint4 xb[4];
+  auto load_x_row = [&](long long xr) {            // this thread's 16-B pieces of source row xr (zeros for xr < 0)
+    if (p.x_dtype == B2H_DT_F32) {
+      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + (size_t)(xr < 0 ? 0 : xr) * n_in);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c < 2 * cpr && ((c >> 1) & 1) == ch) xf[c] = xr < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(src + c);
+    } else {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + (size_t)(xr < 0 ? 0 : xr) * n_in);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < cpr && (c & 1) == ch) xb[c] = xr < 0 ? make_uint4(0, 0, 0, 0) : __ldg(src + c);
+    }
+  };
   auto prefetch_x = [&](int tile) {
     const int gw = tile * wpt + hh * gh + wj;
     const bool valid = (t < T) && (wj < gh) && (gw < p.B) && tile < p.n_tiles;
     if (!fast_in || !valid) return;
-    if (p.x_dtype == B2H_DT_F32) {
-      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + ((size_t)gw * T + t) * n_in);
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        if (c < 2 * cpr && ((c >> 1) & 1) == ch) xf[c] = __ldg(src + c);
-    } else {
-      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + ((size_t)gw * T + t) * n_in);
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        if (c < cpr && (c & 1) == ch) xb[c] = __ldg(src + c);
-    }
+    load_x_row(xrow_of(gw, t));
   };
   prefetch_x(blockIdx.x);
 
@@ -377,19 +396,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       const int pe = g.pos_emb;
       const int nch0 = g.kp[0] / 8;
       if (rc.valid && vec_in) {
-        if (!fast_in) {   // no prefetch (NT > 1): load this row now
-          if (p.x_dtype == B2H_DT_F32) {
-            const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x) + ((size_t)rc.gw * T + rc.t) * n_in);
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              if (c < 2 * cpr && ((c >> 1) & 1) == ch) xf[c] = __ldg(src + c);
-          } else {
-            const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.x) + ((size_t)rc.gw * T + rc.t) * n_in);
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              if (c < cpr && (c & 1) == ch) xb[c] = __ldg(src + c);
-          }
-        }
+        if (!fast_in) load_x_row(xrow_of(rc.gw, rc.t));   // no prefetch (NT > 1): load this row now
         if (p.x_dtype == B2H_DT_F32) {
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8)
@@ -404,6 +411,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
             if (c8 < cpr && (c8 & 1) == ch) *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = xb[c8];
         }
       } else if (rc.valid) {
+        const long long xr = xrow_of(rc.gw, rc.t);
         for (int c8 = ch; c8 < nch0; c8 += 2) {
           float v[8];
 #pragma unroll
@@ -411,8 +419,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
             const int cc = c8 * 8 + e;            // channel in the conv1 input (pos-emb row first)
             float val = 0.0f;
             if (pe && cc == 0) val = __fdiv_rn((float)rc.t, 100.0f);             // HandPoseModels.py:70-82
-            else if (cc - pe < n_in && cc - pe >= 0) {
-              const size_t gi = ((size_t)rc.gw * T + rc.t) * n_in + (cc - pe);
+            else if (cc - pe < n_in && cc - pe >= 0 && xr >= 0) {
+              const size_t gi = (size_t)xr * n_in + (cc - pe);
               val = (p.x_dtype == B2H_DT_F32) ? __ldg(reinterpret_cast<const float*>(p.x) + gi)
                                               : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.x)[gi]);
             }
@@ -945,10 +953,11 @@ void set_debug_timing(long long* p) { g_dbg_timing = p; }
 bool tc_tile_ok(const Geo& g, int T, bool train) { return tc_tile_supported(g, T, train); }
 
 int launch_tc_tile_fwd(const void* x, int x_dtype, const float* params, const char* packed, const int32_t* lengths, float* y,
-                       int B, int T, int apply_mask, float out_scale, const Geo& g, cudaStream_t stream) {
+                       int B, int T, int apply_mask, float out_scale, const Geo& g, cudaStream_t stream, const WindowView* wv) {
   TcTileArgs p{};
   p.x = x; p.x_dtype = x_dtype; p.params = params; p.packed = packed; p.lengths = lengths; p.y = y;
   p.B = B; p.T = T; p.apply_mask = apply_mask; p.mode = 0; p.out_scale = out_scale; p.geo = g;
+  if (wv) { p.win_start = wv->win_start; p.win_end = wv->win_end; p.n_frames = wv->n_frames; p.pad_mode = wv->pad_mode; }
   p.dbg = g_dbg_timing;
   return launch_tc_tile(p, false, stream);
 }

@@ -251,6 +251,40 @@ class ConvModel(nn.Module):
         return self._forward_impl(inp, lengths=lengths, out_scale=1.0 if denormalize is None else float(denormalize))
 
 
+    @torch.no_grad()
+    def predict_windows(self, frames, win_start, T, win_end=None, pad_mode="repeat_first", lengths=None, denormalize=None, out=None):
+        """Streaming inference over sliding windows WITHOUT materialising them: `frames` (F, K, 2) is the per-frame
+        network input of a whole clip (`PreprocessRightHand.frame_stream`), window w covers frames
+        [win_start[w], win_start[w] + T) cut at win_end[w] (default F) and padded by the dataset's rule
+        (text_pose_dataset.py:511-518 repeat-first / :614-622 zeros).  Returns (W, T, 21, 2), identical to
+        `predict` on the materialised (W, T, K, 2) windows.  bf16 mode, conv_channels <= 64, T <= 256."""
+        if not self._is_flat():
+            self._flatten()
+        _lib.require_device(frames, "frames")
+        _lib.require_sm100(frames.device)
+        if frames.dim() != 3 or frames.shape[1] * frames.shape[2] != self.n_in:
+            raise RuntimeError(f"expected frames (F, {self.n_in // 2}, 2), got {tuple(frames.shape)}")
+        if frames.dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError(f"frames must be float32 or bfloat16, got {frames.dtype}")
+        if self.pos_emb is not None and T != self.pos_emb.max_len:
+            raise RuntimeError(f"Sizes of tensors must match: pos_emb requires T == {self.pos_emb.max_len}, got {T}")
+        dev = frames.device
+        x = frames.contiguous()
+        ws = torch.as_tensor(win_start).to(device=dev, dtype=torch.int64).contiguous()
+        we = None if win_end is None else torch.as_tensor(win_end).to(device=dev, dtype=torch.int64).contiguous()
+        W = ws.numel()
+        pm = {"repeat_first": _lib.PAD_REPEAT_FIRST, "zeros": _lib.PAD_ZEROS}[pad_mode]
+        len32 = None if lengths is None else torch.as_tensor(lengths).to(device=dev, dtype=torch.int32).contiguous()
+        n_in, C, pe = self._geometry()
+        y = out if out is not None else torch.empty((W, T, 21, 2), dtype=torch.float32, device=dev)
+        _lib.check(_lib.load().b2h_conv_forward_windows(
+            _lib.ptr(x), _lib.DT_BF16 if x.dtype == torch.bfloat16 else _lib.DT_F32, x.shape[0], _lib.ptr(ws), _lib.ptr(we), pm,
+            _lib.ptr(self._flat), _lib.ptr(self.packed_weights()), _lib.ptr(len32), _lib.ptr(y), W, T, n_in, C, pe,
+            _lib.PRECISIONS[self.precision], 1 if len32 is not None else 0, 1.0 if denormalize is None else float(denormalize),
+            _lib.stream_ptr(dev)))
+        return y
+
+
 def format_prediction(prediction, fmt="openpose"):
     """(..., 21, 2) predictions -> (..., 63) rows in the reference's writer layouts:
     "openpose" = [x,y,1.0]*21 (array2open_pose, steps/utils.py:355-364), "h5" = [x*21 | y*21 | 0*21]

@@ -88,6 +88,32 @@ class PreprocessRightHand:
             out["input_kp_bf16"] = bf.view(W, T, 12, 2)
         return self._alias(out)
 
+    def frame_stream(self, pose25, hand_left, hand_right, dtype=torch.bfloat16, out=None):
+        """Streaming inference (BASELINE config 5): the network input of EVERY UNIQUE FRAME of a clip, once --
+        (F, 12, 2) in `dtype` (bf16 feeds the tensor-core net directly; fp32 is the reference item's `input_kp`).
+        Only what the net reads is written (804 B read + 48 B written per frame in bf16), no targets / confidences.
+        Sliding windows over the clip are then VIEWS of this stream: `ConvModel.predict_windows(stream, starts, T)`
+        applies the crop + pad rule on the fly, so 4x-overlapping windows are neither written nor re-read."""
+        _lib.require_device(pose25, "pose25")
+        _lib.require_sm100(pose25.device)
+        dev = pose25.device
+        F = pose25.shape[0]
+        if tuple(pose25.shape[1:]) != (25, 3) or tuple(hand_left.shape) != (F, 21, 3) or tuple(hand_right.shape) != (F, 21, 3):
+            raise RuntimeError("expected pose25 (F,25,3), hand_left (F,21,3), hand_right (F,21,3)")
+        if dtype not in (torch.bfloat16, torch.float32):
+            raise ValueError("dtype must be torch.bfloat16 or torch.float32")
+        pose25, hand_left, hand_right = (_dev_f32(a, dev) for a in (pose25, hand_left, hand_right))
+        if out is None:
+            out = torch.empty((F, 12, 2), dtype=dtype, device=dev)
+        if getattr(self, "_zero_start", None) is None or self._zero_start.device != dev:
+            self._zero_start = torch.zeros(1, dtype=torch.int64, device=dev)
+        f32 = _lib.ptr(out) if dtype == torch.float32 else None
+        b16 = _lib.ptr(out) if dtype == torch.bfloat16 else None
+        _lib.check(_lib.load().b2h_preprocess(_lib.ptr(pose25), _lib.ptr(hand_left), _lib.ptr(hand_right), F, _lib.ptr(self._zero_start),
+                                              None, 1, F, self.pad_mode, self.factor, int(self.dif_encoding), int(self.normalize),
+                                              f32, None, None, None, None, None, None, b16, _lib.stream_ptr(dev)))
+        return out
+
     def from_h5_rows(self, rows150, win_start, T, win_end=None):
         """Packed rows of TextPoseH5Dataset.array2item (text_pose_dataset.py:587-612): (F,150) =
         [x0..x49|y0..y49|c0..c49]; body = 8 keypoints."""

@@ -88,7 +88,8 @@ int b2h_pack_weights(const float* params, void* packed, int n_in, int C, int pos
  * Inputs: OpenPose rows [x,y,c]: pose25 (F,25,3), hand_left (F,21,3), hand_right (F,21,3) fp32.
  * Window w covers source frames [win_start[w], win_start[w]+T) cut at win_end[w] (nullable: F) -- the end of the
  * utterance it is cropped from when several utterances are packed back to back -- and padded by `pad_mode`.
- * Outputs (W,T,12,2) (W,T,12) (W,T,21,2) (W,T,21) [(W,T,21,2) (W,T,21) nullable] fp32,
+ * Outputs (W,T,12,2) (W,T,12) (W,T,21,2) (W,T,21) [(W,T,21,2) (W,T,21)] fp32, every one nullable (an inference stream
+ * needs only the keypoint input: at least one output or input_kp_bf16 must be given),
  * n_frames_out (W) int64 = min(F - start, T)  (…:447);  input_kp_bf16 nullable (W,T,24) bf16 copy
  * feeding the bf16 net without a second pass. */
 int b2h_preprocess(const float* pose25, const float* hand_left, const float* hand_right, int64_t n_frames,
@@ -118,6 +119,16 @@ int b2h_preprocess_h5(const float* rows150, int64_t n_frames, const int64_t* win
 int b2h_conv_forward(const void* x, int x_dtype, const float* params, const void* packed, const int32_t* lengths,
                      float* y, int B, int T, int n_in, int C, int pos_emb, int precision, int apply_mask,
                      float out_scale, void* stream);
+
+/* ConvModel.forward over WINDOW VIEWS of a per-frame stream (BASELINE config 5: sliding windows over hours of frames).
+ * frames (n_frames, n_in) fp32 or bf16 = the preprocessed keypoints of every unique frame (b2h_preprocess with ONE window
+ * covering the clip); window w, frame t reads row win_start[w] + t, cut at win_end[w] (nullable: n_frames) and padded by
+ * `pad_mode` exactly like b2h_preprocess pads a crop (dataloaders/text_pose_dataset.py:52-68, 511-518, 614-622) -- the
+ * same result as materialising the (n_win, T, n_in) windows first, without writing or re-reading them (stride 16 = 4x
+ * overlap).  y (n_win, T, 42) fp32.  bf16 mode, conv_channels <= 64, T <= 256 (B2H_ESHAPE otherwise). */
+int b2h_conv_forward_windows(const void* frames, int x_dtype, int64_t n_frames, const int64_t* win_start, const int64_t* win_end,
+                             int pad_mode, const float* params, const void* packed, const int32_t* lengths, float* y, int n_win,
+                             int T, int n_in, int C, int pos_emb, int precision, int apply_mask, float out_scale, void* stream);
 
 /* LinearPositionalEmbedding.forward as a stand-alone call (models/HandPoseModels.py:78-84): inp (B, channels, T) fp32
  * -> out (B, channels+1, T) with out[:,0,t] = t / max_len (fp32 division) and the input channels behind it.  Like the

@@ -189,3 +189,39 @@ def test_linear_positional_embedding_forward_matches_reference_semantics():
     assert got.shape == (3, 25, 100) and torch.equal(got.cpu(), want)
     with pytest.raises(RuntimeError):
         pe(torch.zeros(2, 24, 64, device="cuda:0"), None)
+
+
+@pytest.mark.parametrize("pad_mode", ["repeat_first", "zeros"])
+@pytest.mark.parametrize("stride,T", [(64, 64), (16, 64), (7, 37), (50, 200)])
+def test_streaming_window_views_equal_materialised_windows(stride, T, pad_mode):
+    """BASELINE config 5 without re-materialisation: K0 once per unique frame -> (F,12,2) stream; the forward reads
+    sliding windows as VIEWS of it (crop + pad rule on the fly).  Bit-identical to the forward over the windows K0
+    materialises, and within tolerance of the oracle pipeline; the stream itself is the bf16 rounding of the bit-exact
+    reference input."""
+    F = 1000
+    pose, lh, rh = synthetic.synthetic_clip(F, seed=21)
+    starts = b2h.sliding_window_starts(F, T, stride)
+    tp, tl, tr = (torch.from_numpy(a).to(DEV) for a in (pose, lh, rh))
+    pre = b2h.PreprocessRightHand(emit_bf16=True, pad_mode=pad_mode)
+    mat = pre(tp, tl, tr, starts, T)                                                        # materialised windows (reference item)
+    stream = pre.frame_stream(tp, tl, tr)                                                   # (F,12,2) bf16, one row per unique frame
+    one = pre(tp, tl, tr, np.zeros(1, dtype=np.int64), F)
+    assert torch.equal(stream, one["input_kp_bf16"].view(F, 12, 2))
+    assert torch.equal(pre.frame_stream(tp, tl, tr, dtype=torch.float32), one["input_kp"].view(F, 12, 2))
+    sd = oracle.init_params(30, False, seed=0)
+    m = _model(sd, 30, False, "bf16")
+    y_view = m.predict_windows(stream, starts, T, pad_mode=pad_mode, denormalize=1280)
+    y_mat = m.predict(mat["input_kp_bf16"], denormalize=1280)
+    _tc_clean()
+    assert torch.equal(y_view, y_mat)
+    want_item = oracle.preprocess_windows(pose, lh, rh, starts, T,
+                                          pad_mode=oracle.PAD_REPEAT_FIRST if pad_mode == "repeat_first" else oracle.PAD_ZEROS)
+    ref = oracle.conv_model_forward(sd, torch.from_numpy(want_item["input_kp"])).contiguous().numpy() * np.float32(1280)
+    assert oracle.rel_err(y_view.cpu().numpy(), ref) <= TOL["bf16"]
+    # utterance ends inside the stream: windows cut at win_end
+    ends = np.minimum(starts + 45, F).astype(np.int64)
+    y_cut = m.predict_windows(stream, starts, T, win_end=ends, pad_mode=pad_mode)
+    mat_cut = pre(tp, tl, tr, starts, T, win_end=ends)
+    assert torch.equal(y_cut, m.predict(mat_cut["input_kp_bf16"]))
+    with pytest.raises(_lib.B2HError):                                                      # fp32 mode: materialise instead
+        _model(sd, 30, False, "fp32").predict_windows(stream.float(), starts, T)
