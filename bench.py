@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=40)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16", "fp32-ffma"])
     ap.add_argument("--skip-extras", action="store_true", help="only the headline train-step number")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="multi-GPU gradient exchange")
     ap.add_argument("--no-multicast", action="store_true", help="p2p exchange: unicast stores even when an NVLS mapping exists")
@@ -351,7 +351,7 @@ def main():
 
     line = {"metric": "body2hand_train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / timed_steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if train_prec == "fp32" else "bf16", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if train_prec.startswith("fp32") else "bf16", "data": "synthetic",
             "repeats": repeats, "timed_steps": timed_steps, "timed_region_ms": ms,
             "config": {"workload": f"train step (fwd+mask+L1+bwd+Adam), batch {B_TRAIN}x{T} frames per GPU, C={C} (BASELINE config 3/4)",
                        "global_batch": B_TRAIN * world, "frames_per_window": T, "conv_channels": C,
@@ -403,7 +403,7 @@ def main():
         if os.path.isfile(tpath):
             traffic = json.load(open(tpath)).get("train_kernel_dram_bytes_per_launch")
         line["roofline"] = {"bound": "tensor", "achieved": tfl, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tfl / pk["tflops"],
-                            "traffic": traffic, "kernel": "conv_fp32_kernel<train>" if train_prec == "fp32" else "conv_tc_tile_kernel<train>",
+                            "traffic": traffic, "kernel": "conv_fp32_kernel<train>" if train_prec == "fp32-ffma" else "conv_tc_tile_kernel<train>",
                             "kernel_ms": k_ms, "kernel_ms_fwd_bwd_only": k_only_ms, "algorithmic_flop_per_launch": TRAIN_FLOP_PER_WINDOW * B_TRAIN,
                             "peak_source": pk["source"] + ", bf16 dense sustained",
                             "note": "bf16 mode: one cooperative launch per step (fwd+loss+bwd, grid barrier, reduction, Adam), timed over the graph-replayed steps (inter-kernel gaps included); kernel_ms_fwd_bwd_only = the same kernel without its reduction/Adam tail; per-launch device times are in profiles/"}
@@ -428,9 +428,10 @@ def main():
             t_ms = ev0.elapsed_time(ev1) / (reps * slots)
             sm = 24 * Cx + 2 * Cx * Cx + 42 * Cx
             flop = 2 * (5 * Tx - 6) * (3 * sm - 24 * Cx) * Bx
-            return {"value": Bx * Tx / (t_ms * 1e-3), "unit": "frames/s", "ms_per_step": t_ms, "dtype": "f32" if prec == "fp32" else "bf16",
+            return {"value": Bx * Tx / (t_ms * 1e-3), "unit": "frames/s", "ms_per_step": t_ms, "dtype": "f32" if prec.startswith("fp32") else "bf16",
                     "workload": f"train step, batch {Bx}x{Tx}, C={Cx}, CUDA graph", "final_loss": float(rr.loss[0].item()),
-                    "kernel": {1: "ffma", 2: "tcgen05 tile", 5: "tcgen05 wide"}.get(int(lib.b2h_kernel_choice(Tx, 24, Cx, 0, _lib.PRECISIONS[prec], 1)), "?"),
+                    "kernel": {1: "ffma", 2: "tcgen05 tile" + (" (bf16 high/low operand pairs, 3 MMAs per product)" if prec == "fp32" else ""),
+                               5: "tcgen05 wide"}.get(int(lib.b2h_kernel_choice(Tx, 24, Cx, 0, _lib.PRECISIONS[prec], 1)), "?"),
                     "roofline": {"bound": "tensor", "achieved": flop / (t_ms * 1e-3) / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
                                  "frac": flop / (t_ms * 1e-3) / 1e12 / pk["tflops"]}}
 
@@ -452,7 +453,7 @@ def main():
             t_ms = ev0.elapsed_time(ev1) / (reps * slots)
             sm = 24 * Cx + 2 * Cx * Cx + 42 * Cx
             flop = 2 * (5 * Tx - 6) * sm * Bx
-            return {"value": Bx * Tx / (t_ms * 1e-3), "unit": "frames/s", "ms_per_batch": t_ms, "dtype": "f32" if prec == "fp32" else "bf16",
+            return {"value": Bx * Tx / (t_ms * 1e-3), "unit": "frames/s", "ms_per_batch": t_ms, "dtype": "f32" if prec.startswith("fp32") else "bf16",
                     "workload": f"forward, batch {Bx}x{Tx}, C={Cx}, CUDA graph",
                     "roofline": {"bound": "tensor", "achieved": flop / (t_ms * 1e-3) / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
                                  "frac": flop / (t_ms * 1e-3) / 1e12 / pk["tflops"]}}
@@ -462,6 +463,8 @@ def main():
             # default shape (run.py:28,43: batch 128, 200-frame crops) and BASELINE config 1 (one 64-frame window) ----------------
             for key, fn in (("train_fp32", lambda: time_train("fp32", B_TRAIN, T)),
                             ("fwd_fp32", lambda: time_fwd("fp32", B_FWD, T)),
+                            ("train_fp32_ffma", lambda: time_train("fp32-ffma", B_TRAIN, T)),
+                            ("fwd_fp32_ffma", lambda: time_fwd("fp32-ffma", B_FWD, T)),
                             ("train_ref_default_shape", lambda: time_train(train_prec, 128, 200)),
                             ("train_ref_default_shape_fp32", lambda: time_train("fp32", 128, 200)),
                             ("fwd_config1_latency", lambda: time_fwd(fwd_prec, 1, T, slots=4, reps=50)),

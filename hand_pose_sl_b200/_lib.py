@@ -14,11 +14,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2h.so")
 
 # enums of include/b2h.h
-FP32, BF16 = 0, 1
+FP32, BF16, FP32_FFMA = 0, 1, 2
 LOSS_L1, LOSS_CONFL1 = 0, 1
 PAD_REPEAT_FIRST, PAD_ZEROS = 0, 1
 DT_F32, DT_BF16 = 0, 1
-PRECISIONS = {"fp32": FP32, "bf16": BF16}
+PRECISIONS = {"fp32": FP32, "bf16": BF16, "fp32-ffma": FP32_FFMA}
 LOSSES = {"L1": LOSS_L1, "confL1": LOSS_CONFL1}
 
 _SIGNATURES = {

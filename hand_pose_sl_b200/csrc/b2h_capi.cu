@@ -37,20 +37,27 @@ static bool geo_ok(int n_in, int C, int pos_emb, const char* who) {
   return true;
 }
 
-static bool use_tc_train(const Geo& g, int T, int precision) { return precision == B2H_BF16 && tc_tile_ok(g, T, true); }
+// precision -> is it a tensor-core mode, and with bf16 high/low operand pairs (fp32 mode) or plain bf16 operands
+static bool is_split(int precision) { return precision == B2H_FP32; }
+static bool prec_ok(int precision) { return precision == B2H_FP32 || precision == B2H_BF16 || precision == B2H_FP32_FFMA; }
+static bool use_tc_train(const Geo& g, int T, int precision) {
+  return (precision == B2H_BF16 || precision == B2H_FP32) && tc_tile_ok(g, T, true, is_split(precision));
+}
 
 // Which kernel b2h_conv_forward launches (the ONE place that decides; b2h_kernel_choice reports it).
 static int forward_choice(const Geo& g, int T, int precision) {
-  if (precision == B2H_FP32) return fp32_smem_bytes(g, T, false) <= (size_t)226 * 1024 ? B2H_KERNEL_FFMA : B2H_KERNEL_NONE;
+  const int ffma = fp32_smem_bytes(g, T, false) <= (size_t)226 * 1024 ? B2H_KERNEL_FFMA : B2H_KERNEL_NONE;
+  if (precision == B2H_FP32_FFMA) return ffma;
+  if (precision == B2H_FP32) return tc_tile_ok(g, T, false, true) ? B2H_KERNEL_TC_TILE : ffma;   // split tile kernel: C <= 32, T <= 256
   if (precision != B2H_BF16) return B2H_KERNEL_NONE;
-  if (tc_tile_ok(g, T, false)) return B2H_KERNEL_TC_TILE;        // independent 128/256-row tiles (T <= 256, C <= 64)
+  if (tc_tile_ok(g, T, false, false)) return B2H_KERNEL_TC_TILE; // independent 128/256-row tiles (T <= 256, C <= 64)
   if (tc_fwd_supported(g, T)) return B2H_KERNEL_TC_ROWSPACE;     // long windows (T <= 1024, C <= 64): layer-major row space
   if (tc_wide_supported(g, T)) return B2H_KERNEL_TC_WIDE;        // wide models (C <= 256, T <= 256): streamed weights
   return B2H_KERNEL_NONE;
 }
 
 static int train_nparts(const Geo& g, int B, int T, int precision) {
-  return use_tc_train(g, T, precision) ? tc_train_grid(g, B, T) : fp32_train_grid(g, B, T);
+  return use_tc_train(g, T, precision) ? tc_train_grid(g, B, T, is_split(precision)) : fp32_train_grid(g, B, T);
 }
 static int64_t train_part_stride(const Geo& g, int T, int precision) {
   return use_tc_train(g, T, precision) ? gp_total(g) : g.P;
@@ -110,7 +117,7 @@ extern "C" int64_t b2h_packed_bytes(int n_in, int C, int pos_emb) {
 extern "C" int b2h_supported(int T, int n_in, int C, int pos_emb, int precision) {
   if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1) return 0;
   Geo g = make_geo(n_in, C, pos_emb);
-  if (precision == B2H_FP32) return fp32_smem_bytes(g, T, true) <= (size_t)226 * 1024 ? 1 : 0;
+  if (precision == B2H_FP32 || precision == B2H_FP32_FFMA) return fp32_smem_bytes(g, T, true) <= (size_t)226 * 1024 ? 1 : 0;
   if (precision == B2H_BF16) return (tc_fwd_supported(g, T) && fp32_smem_bytes(g, T, true) <= (size_t)226 * 1024) ? 1 : 0;
   return 0;
 }
@@ -122,7 +129,7 @@ extern "C" int b2h_kernel_choice(int T, int n_in, int C, int pos_emb, int precis
   if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1) return B2H_KERNEL_NONE;
   Geo g = make_geo(n_in, C, pos_emb);
   if (!train) return forward_choice(g, T, precision);
-  if (precision != B2H_FP32 && precision != B2H_BF16) return B2H_KERNEL_NONE;
+  if (!prec_ok(precision)) return B2H_KERNEL_NONE;
   if (use_tc_train(g, T, precision)) return B2H_KERNEL_TC_TILE;
   return fp32_smem_bytes(g, T, true) <= (size_t)226 * 1024 ? B2H_KERNEL_FFMA : B2H_KERNEL_NONE;
 }
@@ -154,16 +161,17 @@ extern "C" int b2h_conv_forward(const void* x, int x_dtype, const float* params,
     return B2H_EALIGN;
   }
   Geo g = make_geo(n_in, C, pos_emb);
-  if (precision == B2H_FP32) {
+  if (!prec_ok(precision)) { set_error("b2h_conv_forward: bad precision %d", precision); return B2H_EINVAL; }
+  const int choice = forward_choice(g, T, precision);
+  if (precision == B2H_FP32_FFMA || (precision == B2H_FP32 && choice != B2H_KERNEL_TC_TILE)) {
     Fp32Args a{};
     a.x = x; a.x_dtype = x_dtype; a.lengths = lengths; a.params = params; a.packed = reinterpret_cast<const char*>(packed);
     a.y = y; a.B = B; a.T = T; a.apply_mask = apply_mask; a.mode = 0; a.out_scale = out_scale; a.geo = g;
     return launch_fp32(a, false, (cudaStream_t)stream, 0);
-  } else if (precision == B2H_BF16) {
-    const int choice = forward_choice(g, T, precision);
+  } else {
     if (choice == B2H_KERNEL_TC_TILE)
       return launch_tc_tile_fwd(x, x_dtype, params, reinterpret_cast<const char*>(packed), lengths, y, B, T, apply_mask, out_scale, g,
-                                (cudaStream_t)stream);
+                                (cudaStream_t)stream, nullptr, is_split(precision));
     if (choice == B2H_KERNEL_TC_WIDE)
       return launch_tc_wide_fwd(x, x_dtype, params, reinterpret_cast<const char*>(packed), lengths, y, B, T, apply_mask, out_scale, g,
                                 (cudaStream_t)stream);
@@ -172,8 +180,6 @@ extern "C" int b2h_conv_forward(const void* x, int x_dtype, const float* params,
     a.y = y; a.B = B; a.T = T; a.apply_mask = apply_mask; a.out_scale = out_scale; a.geo = g;
     return launch_tc_fwd(a, (cudaStream_t)stream);
   }
-  set_error("b2h_conv_forward: bad precision %d", precision);
-  return B2H_EINVAL;
 }
 
 extern "C" int b2h_conv_forward_windows(const void* frames, int x_dtype, int64_t n_frames, const int64_t* win_start,
@@ -192,14 +198,14 @@ extern "C" int b2h_conv_forward_windows(const void* frames, int x_dtype, int64_t
     return B2H_EALIGN;
   }
   Geo g = make_geo(n_in, C, pos_emb);
-  if (precision != B2H_BF16 || forward_choice(g, T, precision) != B2H_KERNEL_TC_TILE) {
-    set_error("b2h_conv_forward_windows: window views are served by the tcgen05 tile kernel (bf16 mode, conv_channels <= 64, "
-              "T <= 256); materialise the windows (b2h_preprocess) for C=%d, T=%d, precision=%d", C, T, precision);
+  if ((precision != B2H_BF16 && precision != B2H_FP32) || forward_choice(g, T, precision) != B2H_KERNEL_TC_TILE) {
+    set_error("b2h_conv_forward_windows: window views are served by the tcgen05 tile kernel (conv_channels <= 64 in bf16 mode, "
+              "<= 32 in fp32 mode, T <= 256); materialise the windows (b2h_preprocess) for C=%d, T=%d, precision=%d", C, T, precision);
     return B2H_ESHAPE;
   }
   WindowView wv{reinterpret_cast<const long long*>(win_start), reinterpret_cast<const long long*>(win_end), (long long)n_frames, pad_mode};
   return launch_tc_tile_fwd(frames, x_dtype, params, reinterpret_cast<const char*>(packed), lengths, y, n_win, T, apply_mask, out_scale, g,
-                            (cudaStream_t)stream, &wv);
+                            (cudaStream_t)stream, &wv, is_split(precision));
 }
 
 static int train_common(const void* x, int x_dtype, const float* target, const float* conf, const float* d_y,
@@ -212,7 +218,7 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
   if (x_dtype != B2H_DT_F32 && x_dtype != B2H_DT_BF16) { set_error("%s: bad x_dtype %d", who, x_dtype); return B2H_EINVAL; }
   if (!geo_ok(n_in, C, pos_emb, who)) return B2H_ESHAPE;
   if (B < 1 || T < 1) { set_error("%s: bad B=%d T=%d", who, B, T); return B2H_ESHAPE; }
-  if (precision != B2H_FP32 && precision != B2H_BF16) { set_error("%s: bad precision %d", who, precision); return B2H_EINVAL; }
+  if (!prec_ok(precision)) { set_error("%s: bad precision %d", who, precision); return B2H_EINVAL; }
   if (mode == 1) {
     if (!target || !lengths) { set_error("%s: null target/lengths", who); return B2H_EINVAL; }
     if (loss_kind != B2H_LOSS_L1 && loss_kind != B2H_LOSS_CONFL1) { set_error("%s: bad loss_kind %d", who, loss_kind); return B2H_EINVAL; }
@@ -224,7 +230,7 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
   }
   g = make_geo(n_in, C, pos_emb);
   if (!use_tc_train(g, T, precision) && fp32_smem_bytes(g, T, true) > (size_t)226 * 1024) {
-    set_error("%s: no training kernel for conv_channels=%d, T=%d (tcgen05 training covers C <= 32 and T <= 256 in bf16 mode; "
+    set_error("%s: no training kernel for conv_channels=%d, T=%d (tcgen05 training covers C <= 32 and T <= 256; "
               "the FFMA kernel would need %zu B of shared memory)", who, C, T, fp32_smem_bytes(g, T, true));
     return B2H_ESHAPE;
   }
@@ -250,7 +256,7 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
     fuse->hdr = reinterpret_cast<unsigned*>(workspace);
     a.fuse = *fuse;
   }
-  if (use_tc_train(g, T, precision)) return launch_tc_tile_train(a, stream);
+  if (use_tc_train(g, T, precision)) return launch_tc_tile_train(a, stream, is_split(precision));
   return launch_fp32(a, true, stream, nparts);
 }
 

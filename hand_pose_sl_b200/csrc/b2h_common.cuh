@@ -25,6 +25,8 @@ struct Geo {
   int64_t wd_off[4];        // fp32 dgrad taps     Wd[k'][co][ci]           = W[co][ci][4-k']   (layers 2..4)
   int64_t tf_off[4];        // bf16 UMMA B operand, forward  (blocks of [2][N][8])
   int64_t td_off[4];        // bf16 UMMA B operand, dgrad    (layers 2..4)
+  int64_t tfl_off[4];       // bf16 UMMA B operand, forward, LOW halves: w - bf16(w) rounded to bf16 (fp32 mode on tcgen05:
+                            // x*w ~ x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32 accumulation, ~6e-6 relative)
   int64_t bias_off;         // fp32 [4][64] zero-padded biases (one 1-KB bulk copy into smem)
   int kp[4], np_[4];        // UMMA padded reduction (cin -> mult of 16) and N (cout -> mult of 16), forward
   int64_t packed_bytes;
@@ -54,6 +56,7 @@ __host__ __device__ inline Geo make_geo(int n_in, int C, int pos_emb) {
     g.td_off[l] = b;
     if (l > 0) { b += (int64_t)B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2; b = (b + 127) / 128 * 128; }
   }
+  for (int l = 0; l < 4; ++l) { g.tfl_off[l] = b; b += (int64_t)B2H_KW * g.kp[l] * g.np_[l] * 2; b = (b + 127) / 128 * 128; }
   g.bias_off = b; b += 4 * 64 * 4;
   g.packed_bytes = b;
   return g;
@@ -144,7 +147,9 @@ __device__ __forceinline__ void scatter_packed(const Geo& g, char* packed, int i
   const int ci = rem / B2H_KW, k = rem - ci * B2H_KW;
   reinterpret_cast<float*>(packed + g.wf_off[l])[(k * cin + ci) * cout + co] = v;
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  *reinterpret_cast<__nv_bfloat16*>(packed + g.tf_off[l] + umma_b_offset(k, ci, co, g.kp[l], g.np_[l])) = h;
+  const int64_t bo = umma_b_offset(k, ci, co, g.kp[l], g.np_[l]);
+  *reinterpret_cast<__nv_bfloat16*>(packed + g.tf_off[l] + bo) = h;
+  *reinterpret_cast<__nv_bfloat16*>(packed + g.tfl_off[l] + bo) = __float2bfloat16_rn(v - __bfloat162float(h));
   if (l > 0) {
     reinterpret_cast<float*>(packed + g.wd_off[l])[((B2H_KW - 1 - k) * cout + co) * cin + ci] = v;
     *reinterpret_cast<__nv_bfloat16*>(packed + g.td_off[l] +
@@ -163,7 +168,9 @@ __device__ __forceinline__ void scatter_packed_slot(const Geo& g, char* packed, 
   const int cin = g.cin[l], cout = g.cout[l], co = s.co, ci = s.ci, k = s.k;
   reinterpret_cast<float*>(packed + g.wf_off[l])[(k * cin + ci) * cout + co] = v;
   const __nv_bfloat16 h = __float2bfloat16_rn(v);
-  *reinterpret_cast<__nv_bfloat16*>(packed + g.tf_off[l] + umma_b_offset(k, ci, co, g.kp[l], g.np_[l])) = h;
+  const int64_t bo = umma_b_offset(k, ci, co, g.kp[l], g.np_[l]);
+  *reinterpret_cast<__nv_bfloat16*>(packed + g.tf_off[l] + bo) = h;
+  *reinterpret_cast<__nv_bfloat16*>(packed + g.tfl_off[l] + bo) = __float2bfloat16_rn(v - __bfloat162float(h));
   if (l > 0) {
     reinterpret_cast<float*>(packed + g.wd_off[l])[((B2H_KW - 1 - k) * cout + co) * cin + ci] = v;
     *reinterpret_cast<__nv_bfloat16*>(packed + g.td_off[l] +
@@ -251,12 +258,13 @@ int launch_tc_probe(const void* a, const void* b, float* out, int n, int ksteps,
 int tc_status_and_clear();
 
 struct TcTileArgs;
-int tc_train_grid(const Geo& g, int B, int T);
-bool tc_tile_ok(const Geo& g, int T, bool train);
+int tc_train_grid(const Geo& g, int B, int T, bool split);
+bool tc_tile_ok(const Geo& g, int T, bool train, bool split);   // split = fp32 mode on the tensor pipe (bf16 high/low operand pairs)
 struct WindowView { const long long* win_start; const long long* win_end; long long n_frames; int pad_mode; };
 int launch_tc_tile_fwd(const void* x, int x_dtype, const float* params, const char* packed, const int32_t* lengths, float* y,
-                       int B, int T, int apply_mask, float out_scale, const Geo& g, cudaStream_t stream, const WindowView* wv = nullptr);
-int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream);
+                       int B, int T, int apply_mask, float out_scale, const Geo& g, cudaStream_t stream, const WindowView* wv = nullptr,
+                       bool split = false);
+int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream, bool split = false);
 
 void set_debug_timing(long long* p);
 int launch_tc_bench(long long* out, int M, int N, int reps, int nacc, int mn_major, cudaStream_t stream);

@@ -64,10 +64,14 @@ constexpr int kGatherDepth = 24; // independent 16-B loads in flight per thread 
 constexpr int kDpMaxCta = 160;    // flag slots per rank in the data-parallel exchange buffer (>= CTAs of the train kernel)
 
 struct TileSmem {   // byte offsets into dynamic smem
-  int g0, g1, x, a1, a2, a3, ones, ys, wf[4], wd[4], total;
+  int g0, g1, x, a1, a2, a3, ones, lo_off, ys, has_ys, wf[4], wlo_off, wd[4], total;
 };
 
-__host__ __device__ inline TileSmem tile_smem_layout(const Geo& g, int rows, bool train) {
+// split = fp32 mode on the tensor pipe: every activation / gradient buffer and every forward weight block exists twice
+// (bf16 high half, bf16 low half = bf16(v - high)); the low copies sit at a constant distance (lo_off / wlo_off) behind
+// the high ones.  The dgrad operand blocks are not staged in split mode (the forward blocks are read MN-major instead),
+// nor is the fp32 staging tile of the training kernel (the target rows are read from global memory).
+__host__ __device__ inline TileSmem tile_smem_layout(const Geo& g, int rows, bool train, bool split = false) {
   TileSmem s;
   const int CH = rows * 16;
   int o = 0;
@@ -80,11 +84,17 @@ __host__ __device__ inline TileSmem tile_smem_layout(const Geo& g, int rows, boo
   s.a2 = o; o += (g.kp[1] / 8) * CH;
   s.a3 = o; o += train ? (g.kp[1] / 8) * CH : 0;
   s.ones = o; o += train ? CH : 0;
-  s.ys = o; o += 128 * B2H_COUT * 4;      // fp32 staging rows: y tile on its way out (fwd) / target tile on its way in (train)
+  s.lo_off = split ? o : 0;
+  if (split) o *= 2;
+  s.has_ys = (split && train) ? 0 : 1;
+  s.ys = o; o += s.has_ys ? 128 * B2H_COUT * 4 : 0;   // fp32 staging rows: y tile on its way out (fwd) / target tile on its way in (train)
+  const int w0 = o;
   for (int l = 0; l < 4; ++l) { s.wf[l] = o; o += B2H_KW * g.kp[l] * g.np_[l] * 2; }
+  s.wlo_off = split ? o - w0 : 0;
+  if (split) o += o - w0;
   for (int l = 0; l < 4; ++l) {
     s.wd[l] = o;
-    if (train && l > 0) o += B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2;
+    if (train && l > 0 && !split) o += B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2;
   }
   s.total = o;
   return s;
@@ -95,6 +105,23 @@ __device__ __forceinline__ void store8_bf16(unsigned char* buf, int CH, int row,
   q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
   q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(buf + (size_t)chunk * CH + (size_t)row * 16) = q;
+}
+// split form: high halves to `buf`, low halves bf16(v - high) to buf + lo_off (same position)
+template <bool SPLIT>
+__device__ __forceinline__ void store8_act(unsigned char* buf, int lo_off, int CH, int row, int chunk, const float* v) {
+  uint4 q;
+  q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
+  q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
+  unsigned char* dst = buf + (size_t)chunk * CH + (size_t)row * 16;
+  *reinterpret_cast<uint4*>(dst) = q;
+  if (SPLIT) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      r[i] = pack_bf16x2(v[2 * i] - __uint_as_float(w[i] << 16), v[2 * i + 1] - __uint_as_float(w[i] & 0xFFFF0000u));
+    *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(r[0], r[1], r[2], r[3]);
+  }
 }
 
 __device__ __forceinline__ void bf16x8_to_float(const uint4& q, float* f) {
@@ -112,15 +139,22 @@ __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_b
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 // conv GEMM of one row segment: D[seg rows][N] = sum_{k,s} A[rows + k][16-ch step s] * B_{k,s}
-// a_lo already points at the segment's row 0; rows = buffer rows (chunk stride in 16-B units); b step = N*32 B
+// a_lo already points at the segment's row 0; rows = buffer rows (chunk stride in 16-B units); b step = N*32 B.
+// SPLIT: three MMAs per (tap, k-step) -- A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (al16 / bl16 = distance of the low copies, 16-B units)
+template <bool SPLIT>
 __device__ __forceinline__ void issue_conv(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, int KS, int N,
-                                           int rows, uint32_t idesc) {
+                                           int rows, uint32_t idesc, uint32_t al16 = 0, uint32_t bl16 = 0) {
   uint32_t acc = 0;
 #pragma unroll
   for (int k = 0; k < B2H_KW; ++k) {
     for (int s = 0; s < KS; ++s) {
-      umma_bf16(d_tmem, desc64(a_lo + 2 * s * rows + k, a_hi), desc64(b_lo + (k * KS + s) * 2 * N, b_hi), idesc, acc);
+      const uint32_t a = a_lo + 2 * s * rows + k, b = b_lo + (k * KS + s) * 2 * N;
+      umma_bf16(d_tmem, desc64(a, a_hi), desc64(b, b_hi), idesc, acc);
       acc = 1;
+      if (SPLIT) {
+        umma_bf16(d_tmem, desc64(a + al16, a_hi), desc64(b, b_hi), idesc, 1);
+        umma_bf16(d_tmem, desc64(a, a_hi), desc64(b + bl16, b_hi), idesc, 1);
+      }
     }
   }
 }
@@ -173,7 +207,8 @@ __device__ __forceinline__ long long global_ns() { long long t; asm volatile("mo
 
 // NT (128-row MMA tiles per segment) is a compile-time constant: with it at run time the per-row loops and the row
 // context inside them cost the T <= 128 shapes ~6 % (27.4 -> 29.1 us per train step, 10.5 -> 11.3 us forward).
-template <bool TRAIN, int NT>
+// SPLIT = fp32 mode: bf16 high/low operand pairs, three MMAs per product term group (see tile_smem_layout).
+template <bool TRAIN, int NT, bool SPLIT>
 __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArgs p) {
   int dbg_n = 0;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -190,7 +225,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform
   const int rows = nhalf * HR;
   const int CH = rows * 16;
-  const TileSmem L = tile_smem_layout(g, rows, TRAIN);
+  const TileSmem L = tile_smem_layout(g, rows, TRAIN, SPLIT);
+  const int LO = L.lo_off;                                       // byte distance of the low-half activation copies (SPLIT)
+  const uint32_t al16 = (uint32_t)L.lo_off >> 4, bl16 = (uint32_t)L.wlo_off >> 4;
   unsigned char* G0 = smem + L.g0;
   unsigned char* G1 = smem + L.g1;
   unsigned char* X = smem + L.x;
@@ -222,7 +259,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   const int wj = m / (T + 2), t = m - wj * (T + 2);     // tile 0 (prefetch path, NT == 1)
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
   const int srow = hh * MB + m;                  // row of this thread in the fp32 staging tile
-  const bool bulk_io = (T & 1) == 0 && NT == 1;  // T*168 B and the staging row offsets are 16-B multiples
+  const bool bulk_io = (T & 1) == 0 && NT == 1 && !(SPLIT && TRAIN);  // T*168 B and the staging row offsets are 16-B multiples; the split training kernel has no staging tile
   const int wpt = nhalf * gh;                    // windows per tile
   const int nissue = (nhalf == 2) ? 2 : NT;      // issuing warps: one per row segment / per 128-row MMA tile
   const uint32_t idesc_M = (nhalf == 2) ? 64 : 128;
@@ -279,14 +316,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
     // that run under the buffer zeroing and the first tile's input staging; completion is signalled on wbar.
     uint32_t total = 4 * 64 * 4;
     for (int l = 0; l < 4; ++l) {
-      total += B2H_KW * g.kp[l] * g.np_[l] * 2;
-      if (TRAIN && l > 0) total += B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2;
+      total += B2H_KW * g.kp[l] * g.np_[l] * 2 * (SPLIT ? 2 : 1);
+      if (TRAIN && !SPLIT && l > 0) total += B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2;
     }
     mbar_arrive_expect_tx(&wbar, total);
     bulk_g2s(&bias_s[0][0], p.packed + g.bias_off, 4 * 64 * 4, &wbar);
     for (int l = 0; l < 4; ++l) {
       bulk_g2s(smem + L.wf[l], p.packed + g.tf_off[l], B2H_KW * g.kp[l] * g.np_[l] * 2, &wbar);
-      if (TRAIN && l > 0)
+      if (SPLIT) bulk_g2s(smem + L.wf[l] + L.wlo_off, p.packed + g.tfl_off[l], B2H_KW * g.kp[l] * g.np_[l] * 2, &wbar);
+      if (TRAIN && !SPLIT && l > 0)
         bulk_g2s(smem + L.wd[l], p.packed + g.td_off[l], B2H_KW * round_up(g.cout[l], 16) * round_up(g.cin[l], 16) * 2, &wbar);
     }
   }
@@ -403,12 +441,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
             if (c8 < cpr && (c8 & 1) == ch) {
               const float4 lo = xf[2 * c8], hi = xf[2 * c8 + 1];
               const float v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-              store8_bf16(X, CH, row, c8, v);
+              store8_act<SPLIT>(X, LO, CH, row, c8, v);
             }
         } else {
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8)
-            if (c8 < cpr && (c8 & 1) == ch) *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = xb[c8];
+            if (c8 < cpr && (c8 & 1) == ch) {
+              *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = xb[c8];
+              if (SPLIT) *reinterpret_cast<uint4*>(X + LO + (size_t)c8 * CH + (size_t)row * 16) = make_uint4(0, 0, 0, 0);
+            }
         }
       } else if (rc.valid) {
         const long long xr = xrow_of(rc.gw, rc.t);
@@ -426,11 +467,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
             }
             v[e] = val;
           }
-          store8_bf16(X, CH, row, c8, v);
+          store8_act<SPLIT>(X, LO, CH, row, c8, v);
         }
       } else {
         const uint4 zero = make_uint4(0, 0, 0, 0);
-        for (int c8 = ch; c8 < nch0; c8 += 2) *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = zero;
+        for (int c8 = ch; c8 < nch0; c8 += 2) {
+          *reinterpret_cast<uint4*>(X + (size_t)c8 * CH + (size_t)row * 16) = zero;
+          if (SPLIT) *reinterpret_cast<uint4*>(X + LO + (size_t)c8 * CH + (size_t)row * 16) = zero;
+        }
       }
       if (TRAIN && ch == 0) {   // ones column (B operand of the bias-gradient GEMM): 1 on real frames
         uint4 o = make_uint4(0, 0, 0, 0);
@@ -458,7 +502,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           // output row 2+m of segment h reads input row m+k  ->  start row = h*HR + k
           const uint32_t a_lo = desc_lo(smem_u32(bin), (uint32_t)CH) + warp * seg_row;
           const uint32_t b_lo = desc_lo(smem_u32(smem + L.wf[l]), (uint32_t)N * 16);
-          issue_conv(acc_d + warp * seg_d, a_lo, hi_k, b_lo, hi_k, KS, N, rows, idesc);
+          issue_conv<SPLIT>(acc_d + warp * seg_d, a_lo, hi_k, b_lo, hi_k, KS, N, rows, idesc, al16, bl16);
           umma_commit(&bar);
         }
         __syncwarp();
@@ -483,8 +527,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           float f[16];
 #pragma unroll
           for (int q = 0; q < 16; ++q) f[q] = valid ? fmaxf(__uint_as_float(v[q]) + bias_s[l][c0 + q], 0.0f) : 0.0f;
-          store8_bf16(bout, CH, row, c0 >> 3, f);
-          store8_bf16(bout, CH, row, (c0 >> 3) + 1, f + 8);
+          store8_act<SPLIT>(bout, LO, CH, row, c0 >> 3, f);
+          store8_act<SPLIT>(bout, LO, CH, row, (c0 >> 3) + 1, f + 8);
         }
       } else {
         // layer 4 epilogue: prediction (+ mask_output), and in train mode the criterion and d(loss)/d(pred)
@@ -539,8 +583,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
                 gq[q] = 0.0f;
               }
             }
-            store8_bf16(G0, CH, row, C0 >> 3, gq);
-            store8_bf16(G0, CH, row, (C0 >> 3) + 1, gq + 8);
+            store8_act<SPLIT>(G0, LO, CH, row, C0 >> 3, gq);
+            store8_act<SPLIT>(G0, LO, CH, row, (C0 >> 3) + 1, gq + 8);
           };
           if (ch == 0) { chunk(std::integral_constant<int, 0>{}); chunk(std::integral_constant<int, 32>{}); }
           else chunk(std::integral_constant<int, 16>{});
@@ -600,8 +644,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
             }
           }
           if (TRAIN) {
-            store8_bf16(G0, CH, row, c0 >> 3, gq);
-            store8_bf16(G0, CH, row, (c0 >> 3) + 1, gq + 8);
+            store8_act<SPLIT>(G0, LO, CH, row, c0 >> 3, gq);
+            store8_act<SPLIT>(G0, LO, CH, row, (c0 >> 3) + 1, gq + 8);
           }
           B2H_STAMP();   // layer-4 epilogue: one 16-column chunk done
         }
@@ -641,10 +685,32 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           if (elect_one()) {
             if (l > 0) {  // dgrad: dA_{l-1}[r][ci] = sum_{k',co} dZ_l[r+k'-2][co] * W_l[co][ci][4-k']
               const int KSd = round_up(g.cout[l], 16) >> 4, Nd = round_up(g.cin[l], 16);
-              const uint32_t idesc = make_idesc_bf16(idesc_M, Nd, 0, 0);
               const uint32_t a_lo = desc_lo(smem_u32(gz), (uint32_t)CH) + warp * seg_row;
-              const uint32_t b_lo = desc_lo(smem_u32(smem + L.wd[l]), (uint32_t)Nd * 16);
-              issue_conv(acc_d + warp * seg_d, a_lo, hi_k, b_lo, hi_k, KSd, Nd, rows, idesc);
+              if (!SPLIT) {
+                const uint32_t idesc = make_idesc_bf16(idesc_M, Nd, 0, 0);
+                const uint32_t b_lo = desc_lo(smem_u32(smem + L.wd[l]), (uint32_t)Nd * 16);
+                issue_conv<false>(acc_d + warp * seg_d, a_lo, hi_k, b_lo, hi_k, KSd, Nd, rows, idesc);
+              } else {
+                // No transposed weight blocks in split mode: the FORWARD blocks [tap][ci/8][co row][8 ci] are read as an
+                // MN-major B operand (N = ci: 8-element groups np*16 B apart = SBO; K = co: rows of 16 B, 8-row groups 128 B
+                // apart = LBO), tap k' of the dgrad = forward tap 4-k', K-step s' = co rows 16 s' ..
+                const uint32_t idesc = make_idesc_bf16(idesc_M, Nd, 0, 1);
+                const int KSf = g.kp[l] >> 4, Nf = g.np_[l];
+                const uint32_t hi_w = desc_hi((uint32_t)Nf * 16);
+                const uint32_t b0 = desc_lo(smem_u32(smem + L.wf[l]), 128);
+                uint32_t acc = 0;
+#pragma unroll
+                for (int k = 0; k < B2H_KW; ++k)
+                  for (int sd = 0; sd < KSd; ++sd) {
+                    const uint32_t a = a_lo + 2 * sd * rows + k;
+                    const uint32_t b = b0 + (uint32_t)((B2H_KW - 1 - k) * KSf * Nf * 2 + 16 * sd);
+                    const uint32_t d = acc_d + warp * seg_d;
+                    umma_bf16(d, desc64(a, hi_k), desc64(b, hi_w), idesc, acc);
+                    acc = 1;
+                    umma_bf16(d, desc64(a + al16, hi_k), desc64(b, hi_w), idesc, 1);
+                    umma_bf16(d, desc64(a, hi_k), desc64(b + bl16, hi_w), idesc, 1);
+                  }
+              }
               umma_commit(&bar);
             }
             // wgrad: dW_l[k][co][ci] += sum_r dZ_l[r][co] * in_l[r+k-2][ci];  db_l[co] += sum_r dZ_l[r][co]
@@ -663,8 +729,17 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
 #pragma unroll
                   for (int k = 0; k < B2H_KW + 1; ++k) {
                     if (nissue == 2 && (k & 1) != warp) continue;
-                    if (k < B2H_KW) umma_bf16(dcol + k * 32, ad, desc64(b_lo0 + r0 + k - 2, hi_mn), idw, first);
-                    else umma_bf16(dcol + 5 * 32, ad, desc64(o_lo0 + r0, hi_mn), idb, first);
+                    if (k < B2H_KW) {
+                      const uint64_t bd = desc64(b_lo0 + r0 + k - 2, hi_mn);
+                      umma_bf16(dcol + k * 32, ad, bd, idw, first);
+                      if (SPLIT) {      // dZ_lo * in_hi + dZ_hi * in_lo
+                        umma_bf16(dcol + k * 32, desc64(a_lo0 + r0 + al16, hi_mn), bd, idw, 1);
+                        umma_bf16(dcol + k * 32, ad, desc64(b_lo0 + r0 + k - 2 + al16, hi_mn), idw, 1);
+                      }
+                    } else {
+                      umma_bf16(dcol + 5 * 32, ad, desc64(o_lo0 + r0, hi_mn), idb, first);
+                      if (SPLIT) umma_bf16(dcol + 5 * 32, desc64(a_lo0 + r0 + al16, hi_mn), desc64(o_lo0 + r0, hi_mn), idb, 1);
+                    }
                   }
                 }
               if (l == 0) umma_commit(&bar);     // last MMAs of the tile: fence the buffers before restaging
@@ -694,8 +769,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
             bf16x8_to_float(*reinterpret_cast<const uint4*>(ain + (size_t)((c0 >> 3) + 1) * CH + (size_t)row * 16), act + 8);
 #pragma unroll
             for (int q = 0; q < 16; ++q) f[q] = (valid && act[q] > 0.0f) ? __uint_as_float(v[q]) : 0.0f;
-            store8_bf16(gnext, CH, row, c0 >> 3, f);
-            store8_bf16(gnext, CH, row, (c0 >> 3) + 1, f + 8);
+            store8_act<SPLIT>(gnext, LO, CH, row, c0 >> 3, f);
+            store8_act<SPLIT>(gnext, LO, CH, row, (c0 >> 3) + 1, f + 8);
           }
           }   // MMA tiles j
         }
@@ -783,7 +858,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       const size_t ll_src = ((size_t)(epoch & 1) * f.world + f.rank) * nj;
       // Latency-bound L2 gather of this CTA's `per` slots over all CTA slices: float4 columns x part groups, 16
       // independent 16-B loads in flight per thread, fixed summation order (deterministic).
-      float4* red4 = reinterpret_cast<float4*>(YS);       // [groups][ncol] partial sums (the staging tile is free now)
+      // [groups][ncol] partial sums: the staging tile is free now (split training kernel: the activation buffers are --
+      // every MMA that read them has completed)
+      float4* red4 = reinterpret_cast<float4*>(L.has_ys ? smem + L.ys : smem);
       for (int jb = j0; jb < j_end; jb += 4096) {        // <= 1024 float4 columns (16 KB of staging) per pass
         const int jn = min(j_end, jb + 4096);
         const int ncol = (jn - jb + 3) >> 2;
@@ -890,25 +967,25 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
 }
 
 // ---- host side ----
-inline size_t tc_tile_smem(const Geo& g, int T, bool train) {
+inline size_t tc_tile_smem(const Geo& g, int T, bool train, bool split) {
   const int MB = T <= 64 ? 64 : (T > 128 ? 256 : 128), nhalf = T <= 64 ? 2 : 1;
-  return (size_t)tile_smem_layout(g, nhalf * (MB + 8), train).total;
+  return (size_t)tile_smem_layout(g, nhalf * (MB + 8), train, split).total;
 }
 
-inline bool tc_tile_supported(const Geo& g, int T, bool train) {
+inline bool tc_tile_supported(const Geo& g, int T, bool train, bool split) {
   if (T < 1 || T > 256) return false;
-  if ((g.kp[0] > 32 || g.kp[1] > 32) && (train || g.kp[0] > 64 || g.kp[1] > 64)) return false;
-  return tc_tile_smem(g, T, train) <= (size_t)225 * 1024;
+  if ((g.kp[0] > 32 || g.kp[1] > 32) && (train || split || g.kp[0] > 64 || g.kp[1] > 64)) return false;
+  return tc_tile_smem(g, T, train, split) <= (size_t)225 * 1024;
 }
 
-inline void tc_tile_plan(const Geo& g, int B, int T, bool train, TcTileArgs& p, size_t& smem, int& grid) {
+inline void tc_tile_plan(const Geo& g, int B, int T, bool train, bool split, TcTileArgs& p, size_t& smem, int& grid) {
   if (T <= 64) { p.nhalf = 2; p.MB = 64; p.NT = 1; }
   else { p.nhalf = 1; p.NT = (T > 128) ? 2 : 1; p.MB = 128 * p.NT; }
   p.HR = p.MB + 8;
   p.gh = (p.MB + 2) / (T + 2);
   const int wpt = p.nhalf * p.gh;
   p.n_tiles = (B + wpt - 1) / wpt;
-  smem = (size_t)tile_smem_layout(g, p.nhalf * p.HR, train).total;
+  smem = (size_t)tile_smem_layout(g, p.nhalf * p.HR, train, split).total;
   int per_sm = train ? 1 : (int)((size_t)220 * 1024 / (smem + 2048));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;
@@ -916,21 +993,25 @@ inline void tc_tile_plan(const Geo& g, int B, int T, bool train, TcTileArgs& p, 
   if (grid > p.n_tiles) grid = p.n_tiles;
 }
 
-int tc_train_grid(const Geo& g, int B, int T) {
+int tc_train_grid(const Geo& g, int B, int T, bool split) {
   TcTileArgs p{};
   size_t smem; int grid;
-  tc_tile_plan(g, B, T, true, p, smem, grid);
+  tc_tile_plan(g, B, T, true, split, p, smem, grid);
   return grid;
 }
 
-int launch_tc_tile(TcTileArgs& p, bool train, cudaStream_t stream) {
+int launch_tc_tile(TcTileArgs& p, bool train, bool split, cudaStream_t stream) {
   size_t smem; int grid;
-  tc_tile_plan(p.geo, p.B, p.T, train, p, smem, grid);
+  tc_tile_plan(p.geo, p.B, p.T, train, split, p, smem, grid);
   if (smem > (size_t)225 * 1024) { set_error("tensor-core tile kernel: %zu B shared memory needed", smem); return B2H_ESHAPE; }
-  // four instantiations: {forward, train} x {NT = 1, 2}
+  // eight instantiations: {forward, train} x {NT = 1, 2} x {bf16 operands, bf16 high/low pairs (fp32 mode)}
   const int nt2 = p.NT == 2 ? 1 : 0;
-  const void* fn = train ? (nt2 ? (const void*)conv_tc_tile_kernel<true, 2> : (const void*)conv_tc_tile_kernel<true, 1>)
-                         : (nt2 ? (const void*)conv_tc_tile_kernel<false, 2> : (const void*)conv_tc_tile_kernel<false, 1>);
+  const void* fns[2][2][2] = {
+      {{(const void*)conv_tc_tile_kernel<false, 1, false>, (const void*)conv_tc_tile_kernel<false, 1, true>},
+       {(const void*)conv_tc_tile_kernel<false, 2, false>, (const void*)conv_tc_tile_kernel<false, 2, true>}},
+      {{(const void*)conv_tc_tile_kernel<true, 1, false>, (const void*)conv_tc_tile_kernel<true, 1, true>},
+       {(const void*)conv_tc_tile_kernel<true, 2, false>, (const void*)conv_tc_tile_kernel<true, 2, true>}}};
+  const void* fn = fns[train ? 1 : 0][nt2][split ? 1 : 0];
   if (int rc = ensure_dyn_smem(fn, smem)) return rc;
   void* kargs[] = {&p};
   cudaError_t le;
@@ -950,19 +1031,19 @@ int launch_tc_tile(TcTileArgs& p, bool train, cudaStream_t stream) {
 static long long* g_dbg_timing = nullptr;
 void set_debug_timing(long long* p) { g_dbg_timing = p; }
 
-bool tc_tile_ok(const Geo& g, int T, bool train) { return tc_tile_supported(g, T, train); }
+bool tc_tile_ok(const Geo& g, int T, bool train, bool split) { return tc_tile_supported(g, T, train, split); }
 
 int launch_tc_tile_fwd(const void* x, int x_dtype, const float* params, const char* packed, const int32_t* lengths, float* y,
-                       int B, int T, int apply_mask, float out_scale, const Geo& g, cudaStream_t stream, const WindowView* wv) {
+                       int B, int T, int apply_mask, float out_scale, const Geo& g, cudaStream_t stream, const WindowView* wv, bool split) {
   TcTileArgs p{};
   p.x = x; p.x_dtype = x_dtype; p.params = params; p.packed = packed; p.lengths = lengths; p.y = y;
   p.B = B; p.T = T; p.apply_mask = apply_mask; p.mode = 0; p.out_scale = out_scale; p.geo = g;
   if (wv) { p.win_start = wv->win_start; p.win_end = wv->win_end; p.n_frames = wv->n_frames; p.pad_mode = wv->pad_mode; }
   p.dbg = g_dbg_timing;
-  return launch_tc_tile(p, false, stream);
+  return launch_tc_tile(p, false, split, stream);
 }
 
-int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream) {
+int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream, bool split) {
   TcTileArgs p{};
   p.x = a.x; p.x_dtype = a.x_dtype; p.target = a.target; p.conf = a.conf; p.d_y = a.d_y; p.lengths = a.lengths;
   p.params = a.params; p.packed = a.packed; p.y = a.y; p.partials = a.partials; p.loss_partials = a.loss_partials;
@@ -970,7 +1051,7 @@ int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream) {
   p.out_scale = 1.0f; p.geo = a.geo;
   p.fuse = a.fuse;
   p.dbg = g_dbg_timing;
-  return launch_tc_tile(p, true, stream);
+  return launch_tc_tile(p, true, split, stream);
 }
 
 }  // namespace b2h

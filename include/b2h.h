@@ -27,8 +27,11 @@ extern "C" {
 #define B2H_EWORKSPACE -6 /* workspace too small */
 
 /* precision modes (north_star: fp32 mode 1e-4, bf16 mode 2e-2) */
-#define B2H_FP32 0        /* FFMA, fp32 accumulate everywhere                         */
+#define B2H_FP32 0        /* fp32 mode: tcgen05 with every operand split into bf16 high + low halves, three MMAs per
+                             product (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo), fp32 accumulate in TMEM: ~6e-6 relative on the
+                             prediction (conv_channels <= 32, T <= 256); the FFMA kernel for every other shape */
 #define B2H_BF16 1        /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate (TMEM) */
+#define B2H_FP32_FFMA 2   /* fp32 mode on the CUDA cores only (FFMA, fp32 accumulate): the arbiter of the split kernel */
 
 /* loss kinds -- only the two the reference actually computes (steps/traintest.py:114-117) */
 #define B2H_LOSS_L1     0 /* maskedPoseL1     steps/utils.py:413-428 (batch mean) */
@@ -70,8 +73,9 @@ int b2h_forward_supported(int T, int n_in, int C, int pos_emb, int precision);
 /* Which kernel the forward (train = 0) or the train step (train = 1) runs for this shape -- the dispatch itself uses
  * this function, so a test can pin "the tensor-core path is the one that runs" without a GPU. */
 #define B2H_KERNEL_NONE 0        /* unsupported: the entry point returns B2H_ESHAPE */
-#define B2H_KERNEL_FFMA 1        /* fp32-accumulate FFMA kernel (fp32 mode; bf16-mode training beyond the tile kernel) */
-#define B2H_KERNEL_TC_TILE 2     /* tcgen05 tile kernel, weights resident in shared memory (C <= 64 fwd / 32 train, T <= 256) */
+#define B2H_KERNEL_FFMA 1        /* fp32-accumulate FFMA kernel (B2H_FP32_FFMA; shapes beyond the tile kernel) */
+#define B2H_KERNEL_TC_TILE 2     /* tcgen05 tile kernel, weights resident in shared memory (bf16: C <= 64 fwd / 32 train;
+                                    fp32 mode = bf16 high/low pairs: C <= 32; T <= 256) */
 #define B2H_KERNEL_TC_ROWSPACE 3 /* tcgen05 layer-major row-space forward (C <= 64, T <= 1024) */
 #define B2H_KERNEL_TC_WIDE 4     /* tcgen05 streamed-weight forward (C <= 256, T <= 256) */
 int b2h_kernel_choice(int T, int n_in, int C, int pos_emb, int precision, int train);

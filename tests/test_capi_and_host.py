@@ -69,14 +69,18 @@ def test_gradient_partial_slot_layout_is_a_bijection():
 def test_kernel_choice_pins_the_tensor_core_paths():
     """The dispatch of b2h_conv_forward / the train entry points goes through b2h_kernel_choice: in bf16 mode every
     BASELINE config, the reference default crop (200 frames) and the wide variant run tcgen05 kernels -- no silent
-    FFMA fallback -- and fp32 mode is always the FFMA kernel."""
+    FFMA fallback -- and fp32 mode runs the split-operand tcgen05 kernel wherever it fits."""
     lib = _lib.load()
     NONE, FFMA, TILE, ROWSPACE, WIDE = 0, 1, 2, 3, 4
     fwd = lambda T, C, prec, pe=0: lib.b2h_kernel_choice(T, 24, C, pe, prec, 0)
     trn = lambda T, C, prec, pe=0: lib.b2h_kernel_choice(T, 24, C, pe, prec, 1)
     for T in (1, 9, 64, 100, 126, 128, 129, 200, 256):
         assert fwd(T, 30, _lib.BF16) == TILE and trn(T, 30, _lib.BF16) == TILE, T
-        assert fwd(T, 30, _lib.FP32) == FFMA and trn(T, 30, _lib.FP32) == FFMA, T
+        # fp32 mode = the same tcgen05 tile kernel with bf16 high/low operand pairs (3 MMAs per product); its doubled
+        # activation buffers fit shared memory for training up to 128-frame windows; FFMA is the explicit arbiter mode
+        assert fwd(T, 30, _lib.FP32) == TILE and trn(T, 30, _lib.FP32) == (TILE if T <= 128 else FFMA), T
+        assert fwd(T, 30, _lib.FP32_FFMA) == FFMA and trn(T, 30, _lib.FP32_FFMA) == FFMA, T
+    assert fwd(64, 64, _lib.FP32) == FFMA and trn(64, 64, _lib.FP32) == FFMA                # split covers C <= 32
     assert fwd(100, 30, _lib.BF16, 1) == TILE and trn(100, 30, _lib.BF16, 1) == TILE        # pos_emb: 25 input channels
     assert fwd(64, 64, _lib.BF16) == TILE and trn(64, 64, _lib.BF16) == FFMA                # C > 32 trains on FFMA
     assert fwd(200, 64, _lib.BF16) == ROWSPACE                                              # tile does not fit smem

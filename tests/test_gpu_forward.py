@@ -10,7 +10,7 @@ from conftest import golden_sd, load_golden
 from hand_pose_sl_b200 import _lib, synthetic
 
 pytestmark = pytest.mark.gpu
-TOL = {"fp32": 1e-4, "bf16": 2e-2}
+TOL = {"fp32": 1e-4, "fp32-ffma": 1e-4, "bf16": 2e-2}
 DEV = "cuda:0"
 
 
@@ -25,7 +25,7 @@ def _tc_clean():
     assert _lib.load().b2h_tc_status() == 0, "tensor-core kernel hit a wait timeout"
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp32-ffma", "bf16"])
 @pytest.mark.parametrize("name", ["convmodel_c30_b1.npz", "convmodel_c30.npz", "convmodel_c30_posemb.npz",
                                   "convmodel_c64.npz", "convmodel_c30_t200.npz"])
 def test_forward_golden(name, prec):
