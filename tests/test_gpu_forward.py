@@ -223,5 +223,9 @@ def test_streaming_window_views_equal_materialised_windows(stride, T, pad_mode):
     y_cut = m.predict_windows(stream, starts, T, win_end=ends, pad_mode=pad_mode)
     mat_cut = pre(tp, tl, tr, starts, T, win_end=ends)
     assert torch.equal(y_cut, m.predict(mat_cut["input_kp_bf16"]))
-    with pytest.raises(_lib.B2HError):                                                      # fp32 mode: materialise instead
-        _model(sd, 30, False, "fp32").predict_windows(stream.float(), starts, T)
+    # fp32 mode (split-operand tensor-core kernel) serves window views too; shapes it does not cover must be materialised
+    m32 = _model(sd, 30, False, "fp32")
+    s32 = pre.frame_stream(tp, tl, tr, dtype=torch.float32)
+    assert torch.equal(m32.predict_windows(s32, starts, T, pad_mode=pad_mode), m32.predict(mat["input_kp"]))
+    with pytest.raises(_lib.B2HError):
+        _model(oracle.init_params(64, False, seed=0), 64, False, "fp32").predict_windows(s32, starts, T)
