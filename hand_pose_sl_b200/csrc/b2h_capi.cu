@@ -56,11 +56,32 @@ static int forward_choice(const Geo& g, int T, int precision) {
   return B2H_KERNEL_NONE;
 }
 
-static int train_nparts(const Geo& g, int B, int T, int precision) {
-  return use_tc_train(g, T, precision) ? tc_train_grid(g, B, T, is_split(precision)) : fp32_train_grid(g, B, T);
-}
-static int64_t train_part_stride(const Geo& g, int T, int precision) {
-  return use_tc_train(g, T, precision) ? gp_total(g) : g.P;
+// Which training path serves (B, T, C, precision) and how its workspace is laid out: the ONE place that decides.
+//   [header B2H_WS_HEADER][gradient partials: nparts x stride floats][loss partials: n_loss floats][scratch (wide path)]
+struct TrainPlan {
+  int kernel;            // B2H_KERNEL_TC_TILE | B2H_KERNEL_TC_WIDE_TRAIN | B2H_KERNEL_FFMA | B2H_KERNEL_NONE
+  int nparts, gp_layout, n_loss;
+  int64_t stride, scratch_off, total;
+};
+static TrainPlan train_plan(const Geo& g, int B, int T, int precision) {
+  TrainPlan t{};
+  t.kernel = B2H_KERNEL_NONE;
+  int64_t scratch = 0;
+  if (use_tc_train(g, T, precision)) {
+    t.kernel = B2H_KERNEL_TC_TILE; t.nparts = tc_train_grid(g, B, T, is_split(precision)); t.stride = gp_total(g); t.gp_layout = 1; t.n_loss = t.nparts;
+  } else if (precision == B2H_BF16 && tc_wide_supported(g, T)) {
+    // 32 < conv_channels <= 256: forward+criterion / dgrad chain / split-K wgrad kernels over scratch dumps
+    t.kernel = B2H_KERNEL_TC_WIDE_TRAIN; t.nparts = tc_wide_train_ksplit(g, B, T); t.stride = gp_total(g); t.gp_layout = 1;
+    t.n_loss = tc_wide_train_loss_parts(g, B, T);
+    scratch = tc_wide_train_scratch_bytes(g, B, T);
+  } else if (fp32_smem_bytes(g, T, true) <= (size_t)226 * 1024) {
+    t.kernel = B2H_KERNEL_FFMA; t.nparts = fp32_train_grid(g, B, T); t.stride = g.P; t.gp_layout = 0; t.n_loss = t.nparts;
+  }
+  int64_t o = B2H_WS_HEADER + ((int64_t)t.nparts * t.stride + t.n_loss) * 4;
+  o = (o + 255) / 256 * 256;
+  t.scratch_off = o;
+  t.total = o + scratch + 256;
+  return t;
 }
 
 }  // namespace b2h
@@ -117,9 +138,8 @@ extern "C" int64_t b2h_packed_bytes(int n_in, int C, int pos_emb) {
 extern "C" int b2h_supported(int T, int n_in, int C, int pos_emb, int precision) {
   if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1) return 0;
   Geo g = make_geo(n_in, C, pos_emb);
-  if (precision == B2H_FP32 || precision == B2H_FP32_FFMA) return fp32_smem_bytes(g, T, true) <= (size_t)226 * 1024 ? 1 : 0;
-  if (precision == B2H_BF16) return (tc_fwd_supported(g, T) && fp32_smem_bytes(g, T, true) <= (size_t)226 * 1024) ? 1 : 0;
-  return 0;
+  if (!prec_ok(precision)) return 0;
+  return (forward_choice(g, T, precision) != B2H_KERNEL_NONE && train_plan(g, 1, T, precision).kernel != B2H_KERNEL_NONE) ? 1 : 0;
 }
 extern "C" int b2h_forward_supported(int T, int n_in, int C, int pos_emb, int precision) {
   if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1) return 0;
@@ -130,15 +150,12 @@ extern "C" int b2h_kernel_choice(int T, int n_in, int C, int pos_emb, int precis
   Geo g = make_geo(n_in, C, pos_emb);
   if (!train) return forward_choice(g, T, precision);
   if (!prec_ok(precision)) return B2H_KERNEL_NONE;
-  if (use_tc_train(g, T, precision)) return B2H_KERNEL_TC_TILE;
-  return fp32_smem_bytes(g, T, true) <= (size_t)226 * 1024 ? B2H_KERNEL_FFMA : B2H_KERNEL_NONE;
+  return train_plan(g, 1, T, precision).kernel;
 }
 extern "C" int64_t b2h_workspace_bytes(int B, int T, int n_in, int C, int pos_emb, int precision) {
   if (!geo_ok(n_in, C, pos_emb, "b2h_workspace_bytes")) return B2H_ESHAPE;
   if (B < 1 || T < 1) return B2H_WS_HEADER + 256;
-  Geo g = make_geo(n_in, C, pos_emb);
-  const int np = train_nparts(g, B, T, precision);
-  return B2H_WS_HEADER + ((int64_t)np * train_part_stride(g, T, precision) + np) * 4 + 256;
+  return train_plan(make_geo(n_in, C, pos_emb), B, T, precision).total;
 }
 
 extern "C" int b2h_pack_weights(const float* params, void* packed, int n_in, int C, int pos_emb, void* stream) {
@@ -211,7 +228,7 @@ extern "C" int b2h_conv_forward_windows(const void* frames, int x_dtype, int64_t
 static int train_common(const void* x, int x_dtype, const float* target, const float* conf, const float* d_y,
                         const int32_t* lengths, const float* params, const void* packed, float* pred_out, int B, int T,
                         int n_in, int C, int pos_emb, int loss_kind, int precision, int mode, void* workspace,
-                        int64_t workspace_bytes, cudaStream_t stream, Geo& g, int& nparts, float*& partials,
+                        int64_t workspace_bytes, cudaStream_t stream, Geo& g, TrainPlan& plan, float*& partials,
                         float*& loss_partials, const char* who, long long* step_dev = nullptr, long long* epoch_dev = nullptr,
                         FuseAdam* fuse = nullptr) {
   if (!x || !params || !packed || !workspace) { set_error("%s: null pointer", who); return B2H_EINVAL; }
@@ -229,34 +246,41 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
     return B2H_EALIGN;
   }
   g = make_geo(n_in, C, pos_emb);
-  if (!use_tc_train(g, T, precision) && fp32_smem_bytes(g, T, true) > (size_t)226 * 1024) {
-    set_error("%s: no training kernel for conv_channels=%d, T=%d (tcgen05 training covers C <= 32 and T <= 256; "
-              "the FFMA kernel would need %zu B of shared memory)", who, C, T, fp32_smem_bytes(g, T, true));
+  plan = train_plan(g, B, T, precision);
+  if (plan.kernel == B2H_KERNEL_NONE) {
+    set_error("%s: no training kernel for conv_channels=%d, T=%d, precision=%d (tcgen05 training: C <= 32 in the one-launch tile "
+              "kernel, C <= 256 in bf16 mode through the wide kernels, T <= 256; the FFMA kernel would need %zu B of shared memory)",
+              who, C, T, precision, fp32_smem_bytes(g, T, true));
     return B2H_ESHAPE;
   }
-  nparts = train_nparts(g, B, T, precision);
-  const int64_t stride = train_part_stride(g, T, precision);
-  const int64_t need = B2H_WS_HEADER + ((int64_t)nparts * stride + nparts) * 4;
-  if (workspace_bytes < need) { set_error("%s: workspace %lld B < %lld B", who, (long long)workspace_bytes, (long long)need); return B2H_EWORKSPACE; }
+  const int nparts = plan.nparts;
+  const int64_t stride = plan.stride;
+  if (workspace_bytes < plan.total - 256) { set_error("%s: workspace %lld B < %lld B", who, (long long)workspace_bytes, (long long)plan.total); return B2H_EWORKSPACE; }
   if (reinterpret_cast<uintptr_t>(workspace) & 15) { set_error("%s: workspace must be 16-byte aligned", who); return B2H_EALIGN; }
-  // [header: launch sequence + per-CTA arrival flags of the fused kernel, FIXED offset][gradient partials][loss partials]
+  // [header: launch sequence + per-CTA arrival flags of the fused kernel, FIXED offset][gradient partials][loss partials][scratch]
   partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + B2H_WS_HEADER);
   loss_partials = partials + (size_t)nparts * stride;
-  // fp32 mode: FFMA kernel.  bf16 mode: tcgen05 tile kernel (T <= 256, C <= 32); other bf16 shapes fall
-  // back to the FFMA kernel -- still CUDA, still fp32 master weights.
   Fp32Args a{};
   a.x = x; a.x_dtype = x_dtype; a.target = target; a.conf = conf; a.d_y = d_y; a.lengths = lengths; a.params = params;
   a.packed = reinterpret_cast<const char*>(packed); a.y = pred_out; a.partials = partials; a.loss_partials = loss_partials;
   a.B = B; a.T = T; a.loss_kind = loss_kind; a.apply_mask = 1; a.mode = mode; a.out_scale = 1.0f; a.geo = g;
   a.step_dev = step_dev;
   a.epoch_dev = epoch_dev;
-  if (fuse && use_tc_train(g, T, precision)) {
-    if (nparts > B2H_WS_MAX_CTA) { set_error("%s: %d CTAs exceed the %d arrival flags of the workspace header", who, nparts, B2H_WS_MAX_CTA); return B2H_ESHAPE; }
-    fuse->enabled = 1;
-    fuse->hdr = reinterpret_cast<unsigned*>(workspace);
-    a.fuse = *fuse;
+  if (plan.kernel == B2H_KERNEL_TC_TILE) {
+    if (fuse) {
+      if (nparts > B2H_WS_MAX_CTA) { set_error("%s: %d CTAs exceed the %d arrival flags of the workspace header", who, nparts, B2H_WS_MAX_CTA); return B2H_ESHAPE; }
+      fuse->enabled = 1;
+      fuse->hdr = reinterpret_cast<unsigned*>(workspace);
+      a.fuse = *fuse;
+    }
+    return launch_tc_tile_train(a, stream, is_split(precision));
   }
-  if (use_tc_train(g, T, precision)) return launch_tc_tile_train(a, stream, is_split(precision));
+  if (plan.kernel == B2H_KERNEL_TC_WIDE_TRAIN) {
+    // the device-side counters are bumped by a one-thread kernel-free path: the wide kernels do not touch them, the Adam
+    // kernel reads step_dev -- so advance it here with a tiny launch of the reduce-free counter kernel
+    if (step_dev || epoch_dev) { if (int rc = launch_bump_counters(step_dev, epoch_dev, stream)) return rc; }
+    return launch_tc_wide_train(a, reinterpret_cast<unsigned char*>(workspace) + plan.scratch_off, stream);
+  }
   return launch_fp32(a, true, stream, nparts);
 }
 
@@ -266,12 +290,12 @@ extern "C" int b2h_train_forward_backward(const void* x, int x_dtype, const floa
                                           int C, int pos_emb, int loss_kind, int precision, int64_t* step_dev,
                                           void* workspace, int64_t workspace_bytes, void* stream) {
   if (grads_out && !loss_out) { set_error("b2h_train_forward_backward: null loss_out"); return B2H_EINVAL; }
-  Geo g; int nparts; float *partials, *loss_partials;
+  Geo g; TrainPlan plan; float *partials, *loss_partials;
   int rc = train_common(x, x_dtype, target, conf, nullptr, lengths, params, packed, pred_out, B, T, n_in, C, pos_emb,
-                        loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
+                        loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, plan, partials,
                         loss_partials, "b2h_train_forward_backward", reinterpret_cast<long long*>(step_dev));
   if (rc || !grads_out) return rc;   // grads_out == NULL: only the fused kernel runs, partials stay in the workspace
-  return launch_reduce(partials, nparts, use_tc_train(g, T, precision) ? 1 : 0, g, grads_out, loss_partials, loss_out, (cudaStream_t)stream);
+  return launch_reduce(partials, plan.nparts, plan.gp_layout, g, grads_out, loss_partials, loss_out, (cudaStream_t)stream, nullptr, plan.n_loss);
 }
 
 extern "C" int b2h_train_forward_backward_dp(const void* x, int x_dtype, const float* target, const float* conf,
@@ -280,14 +304,14 @@ extern "C" int b2h_train_forward_backward_dp(const void* x, int x_dtype, const f
                                              int loss_kind, int precision, int64_t* step_dev, int64_t* epoch_dev,
                                              void* workspace, int64_t workspace_bytes, void* stream) {
   if (!sym_grads || !loss_out || !step_dev || !epoch_dev) { set_error("b2h_train_forward_backward_dp: null pointer"); return B2H_EINVAL; }
-  Geo g; int nparts; float *partials, *loss_partials;
+  Geo g; TrainPlan plan; float *partials, *loss_partials;
   int rc = train_common(x, x_dtype, target, conf, nullptr, lengths, params, packed, nullptr, B, T, n_in, C, pos_emb,
-                        loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
+                        loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, plan, partials,
                         loss_partials, "b2h_train_forward_backward_dp", reinterpret_cast<long long*>(step_dev),
                         reinterpret_cast<long long*>(epoch_dev));
   if (rc) return rc;
-  return launch_reduce(partials, nparts, use_tc_train(g, T, precision) ? 1 : 0, g, sym_grads, loss_partials, loss_out,
-                       (cudaStream_t)stream, reinterpret_cast<const long long*>(epoch_dev));
+  return launch_reduce(partials, plan.nparts, plan.gp_layout, g, sym_grads, loss_partials, loss_out,
+                       (cudaStream_t)stream, reinterpret_cast<const long long*>(epoch_dev), plan.n_loss);
 }
 
 extern "C" int b2h_adam_step_dp(float* params, const void* peer_bufs_dev, int rank, int world, float* exp_avg, float* exp_avg_sq,
@@ -319,12 +343,12 @@ extern "C" int b2h_conv_backward(const void* x, int x_dtype, const float* d_y, c
                                  float* grads_out, int B, int T, int n_in, int C, int pos_emb, int precision,
                                  void* workspace, int64_t workspace_bytes, void* stream) {
   if (!grads_out) { set_error("b2h_conv_backward: null output"); return B2H_EINVAL; }
-  Geo g; int nparts; float *partials, *loss_partials;
+  Geo g; TrainPlan plan; float *partials, *loss_partials;
   int rc = train_common(x, x_dtype, nullptr, nullptr, d_y, nullptr, params, packed, nullptr, B, T, n_in, C, pos_emb, 0,
-                        precision, 2, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
+                        precision, 2, workspace, workspace_bytes, (cudaStream_t)stream, g, plan, partials,
                         loss_partials, "b2h_conv_backward");
   if (rc) return rc;
-  return launch_reduce(partials, nparts, use_tc_train(g, T, precision) ? 1 : 0, g, grads_out, nullptr, nullptr, (cudaStream_t)stream);
+  return launch_reduce(partials, plan.nparts, plan.gp_layout, g, grads_out, nullptr, nullptr, (cudaStream_t)stream, nullptr, plan.n_loss);
 }
 
 extern "C" int b2h_train_step(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,
@@ -334,7 +358,7 @@ extern "C" int b2h_train_step(const void* x, int x_dtype, const float* target, c
                               int64_t workspace_bytes, void* stream) {
   if (!exp_avg || !exp_avg_sq || !loss_out) { set_error("b2h_train_step: null pointer"); return B2H_EINVAL; }
   if (step < 1 && !step_dev) { set_error("b2h_train_step: step must be >= 1"); return B2H_EINVAL; }
-  Geo g; int nparts; float *partials, *loss_partials;
+  Geo g; TrainPlan plan; float *partials, *loss_partials;
   // bf16 tile kernel + device-side step counter: ONE cooperative launch (reduction + Adam + re-pack in its tail)
   FuseAdam fuse{};
   fuse.params = params; fuse.m = exp_avg; fuse.v = exp_avg_sq; fuse.packed = reinterpret_cast<char*>(packed);
@@ -342,14 +366,14 @@ extern "C" int b2h_train_step(const void* x, int x_dtype, const float* target, c
   fuse.lr_dev = lr_dev;
   fuse.step_dev = reinterpret_cast<const long long*>(step_dev); fuse.loss_out = loss_out; fuse.world = 1;
   int rc = train_common(x, x_dtype, target, conf, nullptr, lengths, params, packed, nullptr, B, T, n_in, C, pos_emb,
-                        loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
+                        loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, plan, partials,
                         loss_partials, "b2h_train_step", reinterpret_cast<long long*>(step_dev), nullptr,
                         step_dev ? &fuse : nullptr);
   if (rc) return rc;
-  if (step_dev && use_tc_train(g, T, precision)) return B2H_OK;
-  return launch_adam(params, partials, nparts, use_tc_train(g, T, precision) ? 1 : 0, exp_avg, exp_avg_sq, g.P, lr, beta1, beta2, eps, step < 1 ? 1 : step,
+  if (step_dev && plan.kernel == B2H_KERNEL_TC_TILE) return B2H_OK;
+  return launch_adam(params, partials, plan.nparts, plan.gp_layout, exp_avg, exp_avg_sq, g.P, lr, beta1, beta2, eps, step < 1 ? 1 : step,
                      reinterpret_cast<const long long*>(step_dev), lr_dev, 1.0f, packed, g,
-                     loss_partials, loss_out, (cudaStream_t)stream);
+                     loss_partials, loss_out, (cudaStream_t)stream, plan.n_loss);
 }
 
 extern "C" int b2h_train_step_dp(const void* x, int x_dtype, const float* target, const float* conf, const int32_t* lengths,
@@ -363,7 +387,7 @@ extern "C" int b2h_train_step_dp(const void* x, int x_dtype, const float* target
     return B2H_EINVAL;
   }
   if (world < 1 || world > 32 || rank < 0 || rank >= world) { set_error("b2h_train_step_dp: bad rank/world"); return B2H_EINVAL; }
-  Geo g; int nparts; float *partials, *loss_partials;
+  Geo g; TrainPlan plan; float *partials, *loss_partials;
   FuseAdam fuse{};
   fuse.params = params; fuse.m = exp_avg; fuse.v = exp_avg_sq; fuse.packed = reinterpret_cast<char*>(packed);
   fuse.lr = lr; fuse.beta1 = beta1; fuse.beta2 = beta2; fuse.eps = (float)eps; fuse.grad_scale = grad_scale;
@@ -373,13 +397,13 @@ extern "C" int b2h_train_step_dp(const void* x, int x_dtype, const float* target
   fuse.mc_buf = reinterpret_cast<unsigned long long*>(multicast_buf);
   fuse.epoch_dev = reinterpret_cast<const long long*>(epoch_dev); fuse.rank = rank; fuse.world = world;
   int rc = train_common(x, x_dtype, target, conf, nullptr, lengths, params, packed, nullptr, B, T, n_in, C, pos_emb,
-                        loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, nparts, partials,
+                        loss_kind, precision, 1, workspace, workspace_bytes, (cudaStream_t)stream, g, plan, partials,
                         loss_partials, "b2h_train_step_dp", reinterpret_cast<long long*>(step_dev),
                         reinterpret_cast<long long*>(epoch_dev), &fuse);
   if (rc) return rc;
-  if (use_tc_train(g, T, precision)) return B2H_OK;    // everything happened inside the one cooperative launch
-  rc = launch_reduce(partials, nparts, 0, g, sym_grads, loss_partials, loss_out, (cudaStream_t)stream,
-                     reinterpret_cast<const long long*>(epoch_dev));
+  if (plan.kernel == B2H_KERNEL_TC_TILE) return B2H_OK;    // everything happened inside the one cooperative launch
+  rc = launch_reduce(partials, plan.nparts, plan.gp_layout, g, sym_grads, loss_partials, loss_out, (cudaStream_t)stream,
+                     reinterpret_cast<const long long*>(epoch_dev), plan.n_loss);
   if (rc) return rc;
   return launch_adam_dp(params, reinterpret_cast<const float* const*>(peer_bufs_dev), rank, world, exp_avg, exp_avg_sq, g.P, lr,
                         beta1, beta2, eps, reinterpret_cast<const long long*>(step_dev),

@@ -251,6 +251,11 @@ struct TcFwdArgs {
 };
 int launch_tc_fwd(TcFwdArgs& p, cudaStream_t stream);
 bool tc_wide_supported(const Geo& g, int T);
+// wide training (32 < conv_channels <= 256, bf16 mode): forward+criterion / dgrad chain / split-K wgrad over scratch dumps
+int tc_wide_train_ksplit(const Geo& g, int B, int T);          // gradient-partial slices written (= nparts of the reduction)
+int64_t tc_wide_train_scratch_bytes(const Geo& g, int B, int T);
+int tc_wide_train_loss_parts(const Geo& g, int B, int T);
+int launch_tc_wide_train(const Fp32Args& a, unsigned char* scratch, cudaStream_t stream);
 int launch_tc_wide_fwd(const void* x, int x_dtype, const float* params, const char* packed, const int32_t* lengths, float* y,
                        int B, int T, int apply_mask, float out_scale, const Geo& g, cudaStream_t stream);
 bool tc_fwd_supported(const Geo& g, int T);
@@ -270,16 +275,17 @@ void set_debug_timing(long long* p);
 int launch_tc_bench(long long* out, int M, int N, int reps, int nacc, int mn_major, cudaStream_t stream);
 int launch_format_prediction(const float* pred, float* out, int64_t rows, int mode, cudaStream_t stream);
 int launch_pos_emb_concat(const float* inp, float* out, int B, int Cc, int T, int max_len, cudaStream_t stream);
+int launch_bump_counters(long long* step_dev, long long* epoch_dev, cudaStream_t stream);
 int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t stream);
 int launch_reduce(const float* partials, int nparts, int gp_layout, const Geo& g, float* grads, const float* loss_partials,
-                  float* loss_out, cudaStream_t stream, const long long* epoch_dev = nullptr);
+                  float* loss_out, cudaStream_t stream, const long long* epoch_dev = nullptr, int n_loss_parts = -1);
 int launch_adam_dp(float* params, const float* const* peer_bufs, int rank, int world, float* m, float* v, int64_t n, double lr,
                    double beta1, double beta2, double eps, const long long* step_dev, const long long* epoch_dev, const double* lr_dev,
                    float grad_scale, void* packed, const Geo& g, cudaStream_t stream);
 int dp_status_and_clear();
 int launch_adam(float* params, const float* grads, int nparts, int gp_layout, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                 double eps, int64_t step, const long long* step_dev, const double* lr_dev, float grad_scale, void* packed, const Geo& g,
-                const float* loss_partials, float* loss_out, cudaStream_t stream);
+                const float* loss_partials, float* loss_out, cudaStream_t stream, int n_loss_parts = -1);
 int launch_mask_output(float* y, const int32_t* lengths, int B, int T, int row, cudaStream_t stream);
 int launch_pose_l1(const float* pred, const float* target, const float* scores, const int32_t* lengths, int B, int T, int row,
                    int loss_kind, float* loss_out, float* d_pred, float* row_scratch, cudaStream_t stream);

@@ -55,7 +55,8 @@ __device__ __forceinline__ void loss_partial_sum(const float* __restrict__ loss_
 // grads[i] = sum_c partials[c][slot(i)];  loss = sum_c loss_partials[c]
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int nparts, int gp_layout, Geo g,
                                                               float* __restrict__ grads, const float* __restrict__ loss_partials,
-                                                              float* __restrict__ loss_out, const long long* __restrict__ epoch_dev) {
+                                                              float* __restrict__ loss_out, const long long* __restrict__ epoch_dev,
+                                                              int n_loss_parts) {
   __shared__ float red[8][32];
   if (epoch_dev) grads += (size_t)(*epoch_dev & 1) * g.P;      // data parallel: double-buffered exchange slot
   const int nj = gp_layout ? gp_total(g) : g.P;
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     const int i = gp_layout ? flat_index_of_gp(g, j) : j;
     if (i >= 0) grads[i] = s;
   }
-  loss_partial_sum(loss_partials, nparts, loss_out);
+  loss_partial_sum(loss_partials, n_loss_parts, loss_out);
 }
 
 struct AdamArgs {
@@ -77,7 +78,7 @@ struct AdamArgs {
   const long long* step_dev;
   const double* lr_dev;            // nullable: learning rate in device memory (captured graphs follow lr changes)
   char* packed; Geo g;
-  const float* loss_partials; float* loss_out;
+  const float* loss_partials; float* loss_out; int n_loss_parts;
 };
 
 // torch.optim.Adam single-tensor update (defaults: amsgrad=False, weight_decay=0, maximize=False):
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
       if (a.packed) scatter_packed(a.g, a.packed, i, p);
     }
   }
-  loss_partial_sum(a.loss_partials, a.nparts, a.loss_out);
+  loss_partial_sum(a.loss_partials, a.n_loss_parts, a.loss_out);
 }
 
 // ---- data parallel: gradient exchange over peer (NVLink) memory fused with Adam -------------------------------
@@ -324,6 +325,19 @@ int launch_format_prediction(const float* pred, float* out, int64_t rows, int mo
   return check_launch("format_prediction_kernel");
 }
 
+// device-side step / exchange-epoch counters for training paths whose kernels do not bump them themselves (wide path)
+__global__ void bump_counters_kernel(long long* step_dev, long long* epoch_dev) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (step_dev) *step_dev += 1;
+    if (epoch_dev) *epoch_dev += 1;
+  }
+}
+int launch_bump_counters(long long* step_dev, long long* epoch_dev, cudaStream_t stream) {
+  bump_counters_kernel<<<1, 32, 0, stream>>>(step_dev, epoch_dev);
+  count_launch();
+  return check_launch("bump_counters_kernel");
+}
+
 int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t stream) {
   pack_kernel<<<(g.P + 255) / 256, 256, 0, stream>>>(params, reinterpret_cast<char*>(packed), g);
   count_launch();
@@ -331,17 +345,19 @@ int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t st
 }
 
 int launch_reduce(const float* partials, int nparts, int gp_layout, const Geo& g, float* grads, const float* loss_partials,
-                  float* loss_out, cudaStream_t stream, const long long* epoch_dev) {
+                  float* loss_out, cudaStream_t stream, const long long* epoch_dev, int n_loss_parts) {
   const int nj = gp_layout ? gp_total(g) : g.P;
-  reduce_partials_kernel<<<(nj + 31) / 32, 256, 0, stream>>>(partials, nparts, gp_layout, g, grads, loss_partials, loss_out, epoch_dev);
+  reduce_partials_kernel<<<(nj + 31) / 32, 256, 0, stream>>>(partials, nparts, gp_layout, g, grads, loss_partials, loss_out, epoch_dev,
+                                                             n_loss_parts < 0 ? nparts : n_loss_parts);
   count_launch();
   return check_launch("reduce_partials_kernel");
 }
 
 int launch_adam(float* params, const float* grads, int nparts, int gp_layout, float* m, float* v, int64_t n, double lr, double beta1,
                 double beta2, double eps, int64_t step, const long long* step_dev, const double* lr_dev, float grad_scale, void* packed,
-                const Geo& g, const float* loss_partials, float* loss_out, cudaStream_t stream) {
+                const Geo& g, const float* loss_partials, float* loss_out, cudaStream_t stream, int n_loss_parts) {
   AdamArgs a;
+  a.n_loss_parts = n_loss_parts < 0 ? nparts : n_loss_parts;
   a.params = params; a.grads = grads; a.nparts = nparts; a.gp_layout = gp_layout; a.n = n; a.m = m; a.v = v;
   a.beta1 = (float)beta1; a.beta2 = (float)beta2;
   a.one_minus_b1 = (float)(1.0 - beta1); a.one_minus_b2 = (float)(1.0 - beta2);

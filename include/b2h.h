@@ -78,6 +78,9 @@ int b2h_forward_supported(int T, int n_in, int C, int pos_emb, int precision);
                                     fp32 mode = bf16 high/low pairs: C <= 32; T <= 256) */
 #define B2H_KERNEL_TC_ROWSPACE 3 /* tcgen05 layer-major row-space forward (C <= 64, T <= 1024) */
 #define B2H_KERNEL_TC_WIDE 4     /* tcgen05 streamed-weight forward (C <= 256, T <= 256) */
+#define B2H_KERNEL_TC_WIDE_TRAIN 5 /* tcgen05 wide training (32 < C <= 256, T <= 256, bf16 mode): streamed-weight forward that
+                                    saves the layer inputs + criterion, dgrad chain with the transposed blocks, split-K
+                                    weight-gradient GEMMs over the saved operands (three launches + reduce/Adam) */
 int b2h_kernel_choice(int T, int n_in, int C, int pos_emb, int precision, int train);
 
 /* Re-layout the flat fp32 parameters into the packed buffer (run after load_state_dict / any

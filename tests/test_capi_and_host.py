@@ -52,7 +52,8 @@ def test_geometry_queries():
     assert lib.b2h_forward_supported(200, 24, 30, 0, _lib.BF16) == 1
     assert lib.b2h_forward_supported(1000, 24, 30, 0, _lib.BF16) == 1
     assert lib.b2h_forward_supported(1000, 24, 256, 0, _lib.BF16) == 0
-    assert lib.b2h_supported(64, 24, 256, 0, _lib.BF16) == 0          # no tensor-core / FFMA training at C = 256
+    assert lib.b2h_supported(64, 24, 256, 0, _lib.BF16) == 1          # wide training kernels (bf16 mode)
+    assert lib.b2h_supported(64, 24, 256, 0, _lib.FP32) == 0          # fp32 mode: no training kernel at C = 256
     assert lib.b2h_forward_supported(64, 24, 256, 0, _lib.FP32) == 1
 
 
@@ -71,7 +72,7 @@ def test_kernel_choice_pins_the_tensor_core_paths():
     BASELINE config, the reference default crop (200 frames) and the wide variant run tcgen05 kernels -- no silent
     FFMA fallback -- and fp32 mode runs the split-operand tcgen05 kernel wherever it fits."""
     lib = _lib.load()
-    NONE, FFMA, TILE, ROWSPACE, WIDE = 0, 1, 2, 3, 4
+    NONE, FFMA, TILE, ROWSPACE, WIDE, WIDE_TRAIN = 0, 1, 2, 3, 4, 5
     fwd = lambda T, C, prec, pe=0: lib.b2h_kernel_choice(T, 24, C, pe, prec, 0)
     trn = lambda T, C, prec, pe=0: lib.b2h_kernel_choice(T, 24, C, pe, prec, 1)
     for T in (1, 9, 64, 100, 126, 128, 129, 200, 256):
@@ -82,7 +83,7 @@ def test_kernel_choice_pins_the_tensor_core_paths():
         assert fwd(T, 30, _lib.FP32_FFMA) == FFMA and trn(T, 30, _lib.FP32_FFMA) == FFMA, T
     assert fwd(64, 64, _lib.FP32) == FFMA and trn(64, 64, _lib.FP32) == FFMA                # split covers C <= 32
     assert fwd(100, 30, _lib.BF16, 1) == TILE and trn(100, 30, _lib.BF16, 1) == TILE        # pos_emb: 25 input channels
-    assert fwd(64, 64, _lib.BF16) == TILE and trn(64, 64, _lib.BF16) == FFMA                # C > 32 trains on FFMA
+    assert fwd(64, 64, _lib.BF16) == TILE and trn(64, 64, _lib.BF16) == WIDE_TRAIN          # C > 32 trains on the wide tcgen05 kernels
     assert fwd(200, 64, _lib.BF16) == ROWSPACE                                              # tile does not fit smem
     assert fwd(257, 30, _lib.BF16) == ROWSPACE and fwd(1000, 30, _lib.BF16) == ROWSPACE
     assert trn(257, 30, _lib.BF16) == FFMA
@@ -90,7 +91,10 @@ def test_kernel_choice_pins_the_tensor_core_paths():
         for T in (64, 126, 200, 256):
             assert fwd(T, C, _lib.BF16) == WIDE, (T, C)
     assert fwd(300, 256, _lib.BF16) == NONE and fwd(2000, 30, _lib.BF16) == NONE
-    assert trn(64, 256, _lib.BF16) == NONE and trn(64, 256, _lib.FP32) == NONE              # 396 KB of activations
+    for C in (33, 64, 80, 128, 256):
+        for T in (9, 64, 126, 200, 256):
+            assert trn(T, C, _lib.BF16) == WIDE_TRAIN, (T, C)
+    assert trn(300, 256, _lib.BF16) == NONE and trn(64, 256, _lib.FP32) == NONE             # fp32 mode: 396 KB of activations
     assert fwd(64, 256, _lib.FP32) == FFMA
     assert lib.b2h_kernel_choice(64, 24, 30, 0, 7, 0) == NONE                                # bad precision
     for T, C in ((64, 30), (200, 30), (64, 256), (300, 256)):
@@ -99,7 +103,7 @@ def test_kernel_choice_pins_the_tensor_core_paths():
     import ctypes
     buf = (ctypes.c_char * 4096)()
     ptr = ctypes.c_void_p((ctypes.addressof(buf) + 255) // 256 * 256)
-    rc = lib.b2h_train_forward_backward(ptr, 0, ptr, None, ptr, ptr, ptr, ptr, ptr, None, 4, 64, 24, 256, 0, _lib.LOSS_L1, _lib.BF16,
+    rc = lib.b2h_train_forward_backward(ptr, 0, ptr, None, ptr, ptr, ptr, ptr, ptr, None, 4, 64, 24, 256, 0, _lib.LOSS_L1, _lib.FP32,
                                         None, ptr, 1 << 20, None)
     assert rc == -2 and "no training kernel for conv_channels=256" in _lib.last_error()
 

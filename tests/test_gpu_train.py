@@ -412,3 +412,70 @@ def test_fp32_mode_split_kernel_matches_ffma_arbiter():
         assert abs(float(l1) - float(l2)) <= 2e-5 * abs(float(l2))
         assert oracle.rel_err(p1.cpu().numpy(), p2.cpu().numpy()) <= 3e-5
         assert oracle.rel_err(g1.cpu().numpy(), g2.cpu().numpy()) <= 1e-4
+
+
+@pytest.mark.parametrize("kind", ["L1", "confL1"])
+@pytest.mark.parametrize("B,T,C", [(5, 64, 64), (7, 64, 128), (4, 64, 256), (3, 126, 256), (2, 200, 96), (9, 33, 80), (40, 64, 256)])
+def test_wide_training_on_tensor_cores_vs_oracle(B, T, C, kind):
+    """Wide models (32 < conv_channels <= 256, bf16 mode) train on tcgen05: streamed-weight forward that saves the layer
+    inputs + criterion, dgrad chain with the transposed blocks, split-K weight-gradient GEMMs -- against the oracle's
+    literal train step (loss, masked prediction at 2e-2) and against the ideal bf16-operand computation (gradients)."""
+    lib = _lib.load()
+    assert lib.b2h_kernel_choice(T, 24, C, 0, _lib.BF16, 1) == 5
+    sd = oracle.init_params(C, False, seed=B + T)
+    batch = synthetic.model_batch(B, T, seed=7 * B + T, ragged=True, len_seed=T)
+    m = _model(sd, C, False, "bf16")
+    db = {k: (v.to(DEV) if k != "n_frames" else v) for k, v in batch.items()}
+    loss, grads, pred = b2h.forward_backward(m, db, loss=kind, want_pred=True)
+    loss2, grads2 = b2h.forward_backward(m, db, loss=kind)
+    torch.cuda.synchronize()
+    assert lib.b2h_tc_status() == 0
+    assert torch.equal(grads, grads2) and torch.equal(loss, loss2)                           # deterministic split-K reduction
+    st = oracle.TrainState(sd)
+    ref_loss, ref_g = oracle.train_step(st, batch["input_kp"], batch["target_kp"], batch["n_frames"], kind, batch["target_conf"])
+    ref_pred = oracle.mask_output(oracle.conv_model_forward(sd, batch["input_kp"]).contiguous().clone(), batch["n_frames"])
+    assert abs(float(loss) - ref_loss) <= TOL["bf16"] * abs(ref_loss)
+    assert oracle.rel_err(pred.cpu().numpy(), ref_pred.detach().numpy()) <= TOL["bf16"]
+    e_loss, e_g, e_pred = oracle.train_grads_bf16_emulated(sd, batch["input_kp"], batch["target_kp"], batch["n_frames"],
+                                                           kind, batch["target_conf"])
+    assert abs(float(loss) - e_loss) <= 2e-4 * abs(e_loss)
+    assert oracle.rel_err(pred.cpu().numpy(), e_pred.numpy()) <= 3e-3
+    for k, v in _split(m, grads).items():
+        assert oracle.rel_err(v, e_g[k].numpy()) <= 1e-2, k
+
+
+def test_wide_training_fused_steps_follow_the_oracle():
+    """k fused train steps at conv_channels = 128 (wide kernels + reduce/Adam/re-pack) == k reference steps."""
+    C, B, T, steps = 128, 6, 64, 3
+    sd = oracle.init_params(C, False, seed=9)
+    batch = synthetic.model_batch(B, T, seed=41, ragged=True)
+    m = _model(sd, C, False, "bf16")
+    opt = b2h.FusedAdam(m.parameters(), lr=2e-4)
+    db = {k: (v.to(DEV) if k != "n_frames" else v) for k, v in batch.items()}
+    st = oracle.TrainState(sd, lr=2e-4)
+    all_grads = []
+    for s in range(steps):
+        loss = b2h.fused_train_step(m, db, opt)
+        ref_loss, gr = oracle.train_step(st, batch["input_kp"], batch["target_kp"], batch["n_frames"])
+        all_grads.append({k: v.numpy() for k, v in gr.items()})
+        assert abs(float(loss) - ref_loss) <= TOL["bf16"] * abs(ref_loss), s
+    masks = oracle.adam_conditioned(all_grads, sd, 2e-4)
+    want = st.state_dict()
+    for k, v in m.state_dict().items():
+        d = np.abs(v.cpu().numpy() - want[k].numpy())
+        assert d[masks[k]].max() <= TOL["bf16"] * np.abs(want[k].numpy()).max(), k
+        assert d.max() <= 2 * 2e-4 * steps, k
+    packed_by_adam = m._packed.clone()
+    m.mark_packed_stale()
+    assert torch.equal(m.packed_weights(), packed_by_adam)
+    # the runner (device-side step counter, CUDA graph) drives the same path
+    from hand_pose_sl_b200.runner import TrainStepRunner
+    m2 = _model(sd, C, False, "bf16")
+    o2 = b2h.FusedAdam(m2.parameters(), lr=2e-4)
+    r = TrainStepRunner(m2, o2, B, T, "L1")
+    r.load(batch, non_blocking=False)
+    r.capture(1)
+    for s in range(steps):
+        r.replay()
+    r.finish()
+    assert torch.equal(m2.flat_parameters(), m.flat_parameters())
