@@ -431,7 +431,7 @@ def main():
             return {"value": Bx * Tx / (t_ms * 1e-3), "unit": "frames/s", "ms_per_step": t_ms, "dtype": "f32" if prec.startswith("fp32") else "bf16",
                     "workload": f"train step, batch {Bx}x{Tx}, C={Cx}, CUDA graph", "final_loss": float(rr.loss[0].item()),
                     "kernel": {1: "ffma", 2: "tcgen05 tile" + (" (bf16 high/low operand pairs, 3 MMAs per product)" if prec == "fp32" else ""),
-                               5: "tcgen05 wide"}.get(int(lib.b2h_kernel_choice(Tx, 24, Cx, 0, _lib.PRECISIONS[prec], 1)), "?"),
+                               5: "tcgen05 wide (fwd+criterion / dgrad chain / split-K wgrad)"}.get(int(lib.b2h_kernel_choice(Tx, 24, Cx, 0, _lib.PRECISIONS[prec], 1)), "?"),
                     "roofline": {"bound": "tensor", "achieved": flop / (t_ms * 1e-3) / 1e12, "peak": pk["tflops"], "unit": "TFLOP/s",
                                  "frac": flop / (t_ms * 1e-3) / 1e12 / pk["tflops"]}}
 
@@ -465,6 +465,9 @@ def main():
                             ("fwd_fp32", lambda: time_fwd("fp32", B_FWD, T)),
                             ("train_fp32_ffma", lambda: time_train("fp32-ffma", B_TRAIN, T)),
                             ("fwd_fp32_ffma", lambda: time_fwd("fp32-ffma", B_FWD, T)),
+                            ("train_wide", lambda: time_train("bf16", B_TRAIN, T, Cx=256, slots=4, reps=5)),
+                            ("train_wide_c128", lambda: time_train("bf16", B_TRAIN, T, Cx=128, slots=4, reps=5)),
+                            ("train_c64", lambda: time_train("bf16", B_TRAIN, T, Cx=64, slots=4, reps=5)),
                             ("train_ref_default_shape", lambda: time_train(train_prec, 128, 200)),
                             ("train_ref_default_shape_fp32", lambda: time_train("fp32", 128, 200)),
                             ("fwd_config1_latency", lambda: time_fwd(fwd_prec, 1, T, slots=4, reps=50)),
