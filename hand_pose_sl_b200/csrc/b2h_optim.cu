@@ -122,6 +122,59 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
   loss_partial_sum(a.loss_partials, a.n_loss_parts, a.loss_out);
 }
 
+// Large models (wide training: P ~ 740k, a handful of split-K slices): one thread per gradient-partial slot, coalesced
+// loads of the slot from every slice (fixed order -> deterministic), Adam, scatter into the packed operand layouts.
+// (adam_kernel's 32-slots-per-block shape is built for ~20k slots x 128 slices; at 760k slots its 24k blocks cost 400 us.)
+__global__ void __launch_bounds__(256) adam_gp_wide_kernel(AdamArgs a) {
+  __shared__ float s_step_size, s_inv_bc2_sqrt;
+  if (a.step_dev || a.lr_dev) {
+    if (threadIdx.x == 0) {
+      const long long t = a.step_dev ? *a.step_dev : a.step_host;
+      const double lr = a.lr_dev ? *a.lr_dev : a.lr_d;
+      s_step_size = (float)(lr / (1.0 - ipow(a.beta1_d, t)));
+      s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - ipow(a.beta2_d, t)));
+    }
+    __syncthreads();
+    a.step_size = s_step_size;
+    a.inv_bc2_sqrt = s_inv_bc2_sqrt;
+  }
+  const int nj = gp_total(a.g);
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nj) {
+    float gr = 0.f;
+    for (int c = 0; c < a.nparts; ++c) gr += __ldcs(a.grads + (size_t)c * nj + j);
+    GpSlot sl;
+    if (gp_decode(a.g, j, sl)) {
+      const int i = gp_flat_of_slot(a.g, sl);
+      gr *= a.grad_scale;
+      float m = a.m[i], v = a.v[i], p = a.params[i];
+      m = fmaf(gr - m, a.one_minus_b1, m);
+      v = fmaf(a.one_minus_b2 * gr, gr, v * a.beta2);
+      const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
+      p = p - a.step_size * (m / denom);
+      a.m[i] = m; a.v[i] = v; a.params[i] = p;
+      if (a.packed) scatter_packed_slot(a.g, a.packed, sl, p);
+    }
+  }
+  loss_partial_sum(a.loss_partials, a.n_loss_parts, a.loss_out);
+}
+
+// grads[i] = sum_c partials[c][slot(i)] for the same shape of problem (one thread per slot)
+__global__ void __launch_bounds__(256) reduce_gp_wide_kernel(const float* __restrict__ partials, int nparts, Geo g, float* __restrict__ grads,
+                                                             const float* __restrict__ loss_partials, float* __restrict__ loss_out,
+                                                             const long long* __restrict__ epoch_dev, int n_loss_parts) {
+  if (epoch_dev) grads += (size_t)(*epoch_dev & 1) * g.P;
+  const int nj = gp_total(g);
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nj) {
+    float s = 0.f;
+    for (int c = 0; c < nparts; ++c) s += __ldcs(partials + (size_t)c * nj + j);
+    const int i = flat_index_of_gp(g, j);
+    if (i >= 0) grads[i] = s;
+  }
+  loss_partial_sum(loss_partials, n_loss_parts, loss_out);
+}
+
 // ---- data parallel: gradient exchange over peer (NVLink) memory fused with Adam -------------------------------
 // Every rank owns a symmetric buffer  [2][P] fp32 gradients (double-buffered by epoch parity) + [world] uint64 flags.
 // Step protocol (one kernel per rank, all ranks run it concurrently on their own GPU):
@@ -347,6 +400,12 @@ int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t st
 int launch_reduce(const float* partials, int nparts, int gp_layout, const Geo& g, float* grads, const float* loss_partials,
                   float* loss_out, cudaStream_t stream, const long long* epoch_dev, int n_loss_parts) {
   const int nj = gp_layout ? gp_total(g) : g.P;
+  if (gp_layout && nparts <= 16 && nj > 65536) {       // wide training: few slices, many slots
+    reduce_gp_wide_kernel<<<(nj + 255) / 256, 256, 0, stream>>>(partials, nparts, g, grads, loss_partials, loss_out, epoch_dev,
+                                                                n_loss_parts < 0 ? nparts : n_loss_parts);
+    count_launch();
+    return check_launch("reduce_gp_wide_kernel");
+  }
   reduce_partials_kernel<<<(nj + 31) / 32, 256, 0, stream>>>(partials, nparts, gp_layout, g, grads, loss_partials, loss_out, epoch_dev,
                                                              n_loss_parts < 0 ? nparts : n_loss_parts);
   count_launch();
@@ -369,6 +428,11 @@ int launch_adam(float* params, const float* grads, int nparts, int gp_layout, fl
   a.loss_partials = loss_partials; a.loss_out = loss_out;
   a.lr_d = lr; a.beta1_d = beta1; a.beta2_d = beta2; a.step_dev = step_dev; a.lr_dev = lr_dev; a.step_host = step;
   const int64_t nj = gp_layout ? (int64_t)gp_total(g) : n;
+  if (gp_layout && nparts <= 16 && nj > 65536) {       // wide training: few slices, many slots
+    adam_gp_wide_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, stream>>>(a);
+    count_launch();
+    return check_launch("adam_gp_wide_kernel");
+  }
   if (nparts == 1) adam_kernel<<<(unsigned)((nj + 31) / 32), 32, 0, stream>>>(a);
   else adam_kernel<<<(unsigned)((nj + 31) / 32), 256, 0, stream>>>(a);
   count_launch();

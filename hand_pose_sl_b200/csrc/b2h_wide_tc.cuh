@@ -324,6 +324,43 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_kernel(WideArgs 
       for (int l = 0; l < NL; ++l) {
         const int N = p.st[l].N;
         const int layer = p.st[l].layer;      // model layer this stage belongs to (forward: l; backward: 3, 2, 1)
+        // MODE 2: the ReLU mask of this stage (saved input of `layer` > 0) is fetched from the scratch dump and compressed
+        // to bits WHILE the stage's MMAs run -- inside the epilogue loop the 32 dependent global loads per thread cost more
+        // than the accumulator read-out itself.  bit (32 it + 8 i + q) = channel 32 ch + 64 it + 8 i + q of this thread's row.
+        uint32_t mb0[4] = {0u, 0u, 0u, 0u}, mb1[4] = {0u, 0u, 0u, 0u};
+        if (MODE == 2) {
+          const RowCtx rc0 = rowctx(0, tile), rc1 = rowctx(1, tile);
+          const unsigned char* am = dump(tile, p.act_off[layer]);
+          auto pos8 = [](const uint4& a) {      // 8 bf16 -> 8 bits (value > 0)
+            const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+            uint32_t b = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t lo = w[e] & 0xFFFFu, hi = w[e] >> 16;
+              b |= (uint32_t)(((lo & 0x8000u) == 0u) && ((lo & 0x7FFFu) != 0u)) << (2 * e);
+              b |= (uint32_t)(((hi & 0x8000u) == 0u) && ((hi & 0x7FFFu) != 0u)) << (2 * e + 1);
+            }
+            return b;
+          };
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int c0 = 32 * ch + 64 * it;
+            if (c0 < N) {
+              uint4 a0[4], a1[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const bool in = c0 + 8 * i < N;
+                const size_t o0 = (size_t)((c0 >> 3) + i) * CH + (size_t)rc0.row * 16, o1 = (size_t)((c0 >> 3) + i) * CH + (size_t)rc1.row * 16;
+                a0[i] = in ? __ldg(reinterpret_cast<const uint4*>(am + o0)) : make_uint4(0, 0, 0, 0);
+                a1[i] = in ? __ldg(reinterpret_cast<const uint4*>(am + o1)) : make_uint4(0, 0, 0, 0);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { mb0[it] |= pos8(a0[i]) << (8 * i); mb1[it] |= pos8(a1[i]) << (8 * i); }
+            }
+          }
+          if (!rc0.valid) { mb0[0] = mb0[1] = mb0[2] = mb0[3] = 0u; }
+          if (!rc1.valid) { mb1[0] = mb1[1] = mb1[2] = mb1[3] = 0u; }
+        }
         if (!mbar_wait(&acc_full, acc_phase, 63 + l)) return;
         acc_phase ^= 1;
         tc_fence_after();
@@ -335,9 +372,11 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_kernel(WideArgs 
           // MODE 1: a_{l+1} = input of layer l+1 -> ACT[l+1];  MODE 2: dZ_{layer-1} -> DZ[layer-1], masked by the saved
           // input of `layer` (= a_layer = relu output of layer-1)
           unsigned char* dd = MODE == 1 ? dump(tile, p.act_off[l + 1]) : (MODE == 2 ? dump(tile, p.dz_off[layer - 1]) : nullptr);
-          const unsigned char* am = MODE == 2 ? dump(tile, p.act_off[layer]) : nullptr;
           if (MODE != 0) zero_halo(dd, N / 8);
-          for (int c0 = 32 * ch; c0 < N; c0 += 64) {
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int c0 = 32 * ch + 64 * it;
+            if (c0 >= N) break;
             uint32_t v0[32], v1[32];
             tmem_ld32(taddr + c0, v0);
             tmem_ld32(taddr + 256 + c0, v1);
@@ -356,14 +395,10 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_kernel(WideArgs 
                   f1[q] = rc1.valid ? fmaxf(__uint_as_float(v1[8 * i + q]) + bb[q], 0.0f) : 0.0f;
                 }
               } else {
-                float a0[8], a1[8];
-                const size_t o0 = (size_t)((c0 >> 3) + i) * CH + (size_t)rc0.row * 16, o1 = (size_t)((c0 >> 3) + i) * CH + (size_t)rc1.row * 16;
-                bf16x8_to_float(*reinterpret_cast<const uint4*>(am + o0), a0);
-                bf16x8_to_float(*reinterpret_cast<const uint4*>(am + o1), a1);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                  f0[q] = (rc0.valid && a0[q] > 0.0f) ? __uint_as_float(v0[8 * i + q]) : 0.0f;
-                  f1[q] = (rc1.valid && a1[q] > 0.0f) ? __uint_as_float(v1[8 * i + q]) : 0.0f;
+                  f0[q] = ((mb0[it] >> (8 * i + q)) & 1u) ? __uint_as_float(v0[8 * i + q]) : 0.0f;
+                  f1[q] = ((mb1[it] >> (8 * i + q)) & 1u) ? __uint_as_float(v1[8 * i + q]) : 0.0f;
                 }
               }
               const uint4 q0 = pack8(f0), q1 = pack8(f1);
@@ -486,8 +521,9 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_kernel(WideArgs 
 // a ones column) in TMEM.  Work item = (layer, co block, ci block); every item is split over `ksplit` CTAs by tile range;
 // each CTA writes its accumulators once into its slice of the partials workspace in the gradient-partial slot layout
 // (b2h_common.cuh gp_*), which the Adam / reduce kernels sum in fixed order (deterministic).
-// Pipeline: one producer thread streams the tile's A / B pieces (contiguous runs of chunks) with 1-D bulk copies into a
-// 2-stage ring; one thread issues the MMAs; 4 warps read the accumulators out at the end.
+// Pipeline: one producer thread streams the tile's A / B pieces (contiguous runs of chunks) into a 2-stage ring with TMA
+// tensor-map loads (the scratch viewed as rows of 128 B, box = 4 chunks = 132 rows; 1-D bulk copies top out at
+// ~23 B/cycle/SM, below the 32 B/cycle the MMAs consume); one thread issues the MMAs; 4 warps read the accumulators out.
 struct WgradItem { int l, m0, M, n0, N, with_bias; };
 constexpr int kWgMaxItems = 48;
 struct WgradArgs {
@@ -504,8 +540,11 @@ constexpr int kWgABytes = 16 * kWgChunkB; // A piece: up to 16 chunks (M = 128)
 constexpr int kWgBBytes = 8 * kWgChunkB;  // B piece: up to 8 chunks (N = 64)
 constexpr int kWgStageBytes = kWgABytes + kWgBBytes;
 constexpr int kWgBiasCol = 5 * 64;
+constexpr int kWgBoxChunks = 4;           // chunks per TMA box
+constexpr int kWgBoxRows = kWgBoxChunks * kWgChunkB / 128;   // 132 rows of 128 B
+constexpr int kWgBoxBytes = kWgBoxChunks * kWgChunkB;
 
-__global__ void __launch_bounds__(kWgThreads, 1) conv_tc_wide_wgrad_kernel(WgradArgs p) {
+__global__ void __launch_bounds__(kWgThreads, 1) conv_tc_wide_wgrad_kernel(WgradArgs p, const __grid_constant__ CUtensorMap smap) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], done_bar;
   __shared__ uint32_t tmem_slot;
@@ -545,23 +584,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_tc_wide_wgrad_kernel(Wgrad
   const uint32_t tbase = tmem_slot;
   const int a_chunks = min(it.M / 8, g.np_[it.l] / 8 - it.m0 / 8);
   const int b_chunks = min(it.N / 8, g.kp[it.l] / 8 - it.n0 / 8);
-  const uint32_t a_bytes = (uint32_t)a_chunks * kWgChunkB, b_bytes = (uint32_t)b_chunks * kWgChunkB;
+  const int a_boxes = (a_chunks + kWgBoxChunks - 1) / kWgBoxChunks, b_boxes = (b_chunks + kWgBoxChunks - 1) / kWgBoxChunks;
 
   if (warp == 0) {
     if (elect_one()) {
       uint32_t ph = 1;
       int s = 0;
+      const uint32_t full0 = smem_u32(&full_bar[0]);
       for (int tile = t0; tile < t1; ++tile) {
         if (!mbar_wait(&empty_bar[s], ph, 70)) break;
-        const unsigned char* base = p.scratch + (size_t)tile * p.tile_bytes;
-        const unsigned char* asrc = base + p.dz_off[it.l] + (size_t)(it.m0 / 8) * kWgChunkB;
-        const unsigned char* bsrc = base + p.act_off[it.l] + (size_t)(it.n0 / 8) * kWgChunkB;
-        unsigned char* st = smem + (size_t)s * kWgStageBytes;
-        mbar_arrive_expect_tx(&full_bar[s], a_bytes + b_bytes);
-        for (uint32_t o = 0; o < a_bytes; o += 4 * kWgChunkB)      // <= 16.5 KB per bulk copy
-          bulk_g2s(st + o, asrc + o, min(a_bytes - o, (uint32_t)(4 * kWgChunkB)), &full_bar[s]);
-        for (uint32_t o = 0; o < b_bytes; o += 4 * kWgChunkB)
-          bulk_g2s(st + kWgABytes + o, bsrc + o, min(b_bytes - o, (uint32_t)(4 * kWgChunkB)), &full_bar[s]);
+        // 128-byte row of the tile's A / B piece in the scratch tensor (every offset is a multiple of one chunk = 33 rows)
+        const long long base = (long long)tile * p.tile_bytes;
+        const int arow = (int)((base + p.dz_off[it.l] + (long long)(it.m0 / 8) * kWgChunkB) >> 7);
+        const int brow = (int)((base + p.act_off[it.l] + (long long)(it.n0 / 8) * kWgChunkB) >> 7);
+        const uint32_t st = smem_u32(smem + (size_t)s * kWgStageBytes);
+        expect_tx_addr(full0 + s * 8, (uint32_t)(a_boxes + b_boxes) * kWgBoxBytes);      // a box past the tensor end is zero-filled, still counted
+        for (int b = 0; b < a_boxes; ++b) tma_load_2d_addr(st + b * kWgBoxBytes, &smap, 0, arow + b * kWgBoxRows, full0 + s * 8);
+        for (int b = 0; b < b_boxes; ++b) tma_load_2d_addr(st + kWgABytes + b * kWgBoxBytes, &smap, 0, brow + b * kWgBoxRows, full0 + s * 8);
         if (++s == 2) { s = 0; ph ^= 1; }
       }
     }
@@ -648,7 +687,7 @@ bool tc_wide_supported(const Geo& g, int T) {
 }
 
 // tensor map over a run of packed UMMA weight sections viewed as rows of 64 bf16 (128 B), box = 128 rows (one ring stage)
-static int wide_weight_map(const char* base, int64_t bytes, CUtensorMap* out) {
+static int wide_weight_map(const char* base, int64_t bytes, CUtensorMap* out, int box_rows = kWideBoxRows) {
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -662,7 +701,7 @@ static int wide_weight_map(const char* base, int64_t bytes, CUtensorMap* out) {
   }
   const cuuint64_t gdim[2] = {64, (cuuint64_t)(bytes >> 7)};
   const cuuint64_t gstride[1] = {128};
-  const cuuint32_t box[2] = {64, kWideBoxRows};
+  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<char*>(base), gdim, gstride, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -786,7 +825,9 @@ int launch_tc_wide_train(const Fp32Args& a, unsigned char* scratch, cudaStream_t
   w.ksplit = tc_wide_train_ksplit(g, a.B, a.T);
   const size_t wsmem = (size_t)2 * kWgStageBytes + 2 * kWgChunkB;
   if (int rc = ensure_dyn_smem(reinterpret_cast<const void*>(conv_tc_wide_wgrad_kernel), wsmem)) return rc;
-  conv_tc_wide_wgrad_kernel<<<w.n_items * w.ksplit, kWgThreads, wsmem, stream>>>(w);
+  CUtensorMap smap;
+  if (int rc = wide_weight_map(reinterpret_cast<const char*>(scratch), (int64_t)p.n_tiles * p.tile_bytes, &smap, kWgBoxRows)) return rc;
+  conv_tc_wide_wgrad_kernel<<<w.n_items * w.ksplit, kWgThreads, wsmem, stream>>>(w, smap);
   count_launch();
   return check_launch("conv_tc_wide_wgrad_kernel");
 }
