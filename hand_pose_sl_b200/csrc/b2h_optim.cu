@@ -400,7 +400,7 @@ int launch_pack(const float* params, void* packed, const Geo& g, cudaStream_t st
 int launch_reduce(const float* partials, int nparts, int gp_layout, const Geo& g, float* grads, const float* loss_partials,
                   float* loss_out, cudaStream_t stream, const long long* epoch_dev, int n_loss_parts) {
   const int nj = gp_layout ? gp_total(g) : g.P;
-  if (gp_layout && nparts <= 16 && nj > 65536) {       // wide training: few slices, many slots
+  if (gp_layout && nparts <= 64) {                     // few slices (wide training, small batches): one thread per slot
     reduce_gp_wide_kernel<<<(nj + 255) / 256, 256, 0, stream>>>(partials, nparts, g, grads, loss_partials, loss_out, epoch_dev,
                                                                 n_loss_parts < 0 ? nparts : n_loss_parts);
     count_launch();
@@ -428,7 +428,7 @@ int launch_adam(float* params, const float* grads, int nparts, int gp_layout, fl
   a.loss_partials = loss_partials; a.loss_out = loss_out;
   a.lr_d = lr; a.beta1_d = beta1; a.beta2_d = beta2; a.step_dev = step_dev; a.lr_dev = lr_dev; a.step_host = step;
   const int64_t nj = gp_layout ? (int64_t)gp_total(g) : n;
-  if (gp_layout && nparts <= 16 && nj > 65536) {       // wide training: few slices, many slots
+  if (gp_layout && nparts <= 64) {                     // few slices (wide training, small batches): one thread per slot
     adam_gp_wide_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, stream>>>(a);
     count_launch();
     return check_launch("adam_gp_wide_kernel");
