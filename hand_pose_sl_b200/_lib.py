@@ -37,6 +37,7 @@ _SIGNATURES = {
     "b2h_preprocess": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int,
                                c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
+    "b2h_preprocess_status": (c_int, []),
     "b2h_verify_fastdiv": (c_int, [c_float, c_void_p, c_void_p]),
     "b2h_preprocess_h5": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

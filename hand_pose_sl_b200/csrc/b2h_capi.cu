@@ -30,7 +30,7 @@ int check_launch(const char* what) {
 void count_launch(int n) { g_launches.fetch_add(n); }
 
 static bool geo_ok(int n_in, int C, int pos_emb, const char* who) {
-  if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || (pos_emb != 0 && pos_emb != 1)) {
+  if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || pos_emb < 0 || pos_emb > 65536) {
     set_error("%s: unsupported geometry n_in=%d C=%d pos_emb=%d", who, n_in, C, pos_emb);
     return false;
   }
@@ -136,17 +136,17 @@ extern "C" int64_t b2h_packed_bytes(int n_in, int C, int pos_emb) {
   return make_geo(n_in, C, pos_emb).packed_bytes;
 }
 extern "C" int b2h_supported(int T, int n_in, int C, int pos_emb, int precision) {
-  if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1) return 0;
+  if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1 || pos_emb < 0 || pos_emb > 65536) return 0;
   Geo g = make_geo(n_in, C, pos_emb);
   if (!prec_ok(precision)) return 0;
   return (forward_choice(g, T, precision) != B2H_KERNEL_NONE && train_plan(g, 1, T, precision).kernel != B2H_KERNEL_NONE) ? 1 : 0;
 }
 extern "C" int b2h_forward_supported(int T, int n_in, int C, int pos_emb, int precision) {
-  if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1) return 0;
+  if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1 || pos_emb < 0 || pos_emb > 65536) return 0;
   return forward_choice(make_geo(n_in, C, pos_emb), T, precision) != B2H_KERNEL_NONE ? 1 : 0;
 }
 extern "C" int b2h_kernel_choice(int T, int n_in, int C, int pos_emb, int precision, int train) {
-  if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1) return B2H_KERNEL_NONE;
+  if (n_in < 1 || n_in > 64 || C < 1 || C > B2H_MAX_C || T < 1 || pos_emb < 0 || pos_emb > 65536) return B2H_KERNEL_NONE;
   Geo g = make_geo(n_in, C, pos_emb);
   if (!train) return forward_choice(g, T, precision);
   if (!prec_ok(precision)) return B2H_KERNEL_NONE;

@@ -16,7 +16,8 @@ __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m *
 
 // Layout of the flat fp32 parameter buffer (state_dict order) and of the packed weight buffer.
 struct Geo {
-  int n_in, C, pos_emb;
+  int n_in, C, pos_emb;     // pos_emb: 0 / 1 (the positional row t / pe_len in front of the input channels)
+  int pe_len;               // LinearPositionalEmbedding(max_len): 100 in the reference (HandPoseModels.py:23)
   int cin[4], cout[4];
   int w_off[4], b_off[4];   // float offsets into the flat parameter buffer
   int P;                    // total parameter count
@@ -34,7 +35,8 @@ struct Geo {
 
 __host__ __device__ inline Geo make_geo(int n_in, int C, int pos_emb) {
   Geo g;
-  g.n_in = n_in; g.C = C; g.pos_emb = pos_emb;
+  // `pos_emb` of the C-ABI: 0 = off, 1 = on with the reference's max_len = 100, n > 1 = on with max_len = n
+  g.n_in = n_in; g.C = C; g.pos_emb = pos_emb ? 1 : 0; g.pe_len = pos_emb > 1 ? pos_emb : 100;
   g.cin[0] = n_in + (pos_emb ? 1 : 0); g.cout[0] = C;
   g.cin[1] = C; g.cout[1] = C;
   g.cin[2] = C; g.cout[2] = C;

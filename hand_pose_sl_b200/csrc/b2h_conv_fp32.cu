@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kThreads) conv_fp32_kernel(Fp32Args p) {
       }
     }
     if (pe) {   // LinearPositionalEmbedding: channel 0 = t / 100 (fp32 divide)   HandPoseModels.py:70-82
-      for (int t = threadIdx.x; t < T; t += kThreads) X[(t + 2) * ld0] = __fdiv_rn((float)t, 100.0f);
+      for (int t = threadIdx.x; t < T; t += kThreads) X[(t + 2) * ld0] = __fdiv_rn((float)t, (float)g.pe_len);
     }
     __syncthreads();
     conv_rows<0>(X, ld0, g.cin[0], Wf[0], g.cout[0], bias[0], A1, ldc, nullptr, 0, T);   // HandPoseModels.py:55

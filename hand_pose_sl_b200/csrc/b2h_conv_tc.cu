@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_fwd_kernel(TcFwdArgs p)
         for (int i = tid; i < nwin * T; i += kTcThreads) {
           const int gi = i / T, t = i - gi * T;
           const int row = 2 + gi * (T + 2) + t;
-          *reinterpret_cast<__nv_bfloat16*>(buf0 + (size_t)row * 16) = __float2bfloat16_rn(__fdiv_rn((float)t, 100.0f));
+          *reinterpret_cast<__nv_bfloat16*>(buf0 + (size_t)row * 16) = __float2bfloat16_rn(__fdiv_rn((float)t, (float)g.pe_len));
         }
       }
     }

@@ -22,6 +22,9 @@
 namespace b2h {
 
 constexpr int kWarpsPerBlock = 4;
+// set when a wait for a staged 4-frame group (TMA bulk copy) exceeded its ~2 s budget: the launch's outputs are then
+// incomplete; read and cleared by b2h_preprocess_status()
+__device__ int g_pre_status = 0;
 
 template <int FMT> struct Fmt;
 // FMT 0: OpenPose [x,y,c] rows: pose25 (75) | hand_left (63) | hand_right (63)
@@ -289,7 +292,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) preprocess_kernel(PreA
       const uint32_t parity = (uint32_t)(it >> 1) & 1u;
       const long long t0 = clock64();
       while (!tc::mbar_try_wait(&sbar[wib][b], parity))
-        if (clock64() - t0 > 4000000000LL) break;   // never spin forever (a wrong answer is caught by the tests)
+        if (clock64() - t0 > 4000000000LL) {        // never spin forever: record the failure (b2h_preprocess_status) and go on
+          atomicExch(&g_pre_status, 1);
+          break;
+        }
     }
     const float* st = stage_all[wib][b];
     const char* stb = reinterpret_cast<const char*>(st);
@@ -371,6 +377,13 @@ static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 }  // namespace b2h
 
 using namespace b2h;
+
+extern "C" int b2h_preprocess_status(void) {
+  int v = 0, z = 0;
+  cudaMemcpyFromSymbol(&v, g_pre_status, sizeof(int));
+  if (v) cudaMemcpyToSymbol(g_pre_status, &z, sizeof(int));
+  return v;
+}
 
 extern "C" int b2h_verify_fastdiv(float factor, unsigned long long* mismatches_dev, void* stream) {
   if (!mismatches_dev) { set_error("b2h_verify_fastdiv: null pointer"); return B2H_EINVAL; }

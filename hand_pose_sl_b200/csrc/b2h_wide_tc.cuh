@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_kernel(WideArgs 
               for (int e = 0; e < 8; ++e) {
                 const int cc = c8 * 8 + e;          // channel in the conv1 input (pos-emb row first)
                 float val = 0.0f;
-                if (pe && cc == 0) val = __fdiv_rn((float)rc.t, 100.0f);             // HandPoseModels.py:70-82
+                if (pe && cc == 0) val = __fdiv_rn((float)rc.t, (float)g.pe_len);             // HandPoseModels.py:70-82
                 else if (cc - pe < n_in && cc - pe >= 0)
                   val = (p.x_dtype == B2H_DT_F32) ? __ldg(reinterpret_cast<const float*>(p.x) + base + (cc - pe))
                                                   : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.x)[base + (cc - pe)]);

@@ -66,11 +66,18 @@ class _ConvForward(torch.autograd.Function):
 
 
 class ConvModel(nn.Module):
-    def __init__(self, conv_channels, activation, pos_emb, precision="fp32", n_keypoints=12):
+    def __init__(self, conv_channels, activation, pos_emb, precision="fp32", n_keypoints=12, pos_emb_max_len=100,
+                 pos_emb_any_length=False):
+        """Reference signature `ConvModel(conv_channels, activation, pos_emb)` (HandPoseModels.py:18) + extensions:
+        `precision`; `n_keypoints` (input keypoints: 12 in run.py, 8 for the H5 items); and for SURVEY 8f N4
+        `pos_emb_max_len` (LinearPositionalEmbedding(max_len), 100 in the reference) / `pos_emb_any_length=True`, which
+        lifts the reference's T == max_len restriction (its torch.cat fails otherwise): the kernels generate the row
+        t / max_len for whatever window length they are given."""
         super().__init__()
         n_in = n_keypoints * 2
+        self.pos_emb_any_length = bool(pos_emb_any_length)
         if pos_emb:
-            self.pos_emb = LinearPositionalEmbedding(max_len=100)                          # HandPoseModels.py:23
+            self.pos_emb = LinearPositionalEmbedding(max_len=int(pos_emb_max_len))          # HandPoseModels.py:23
             self.conv1 = nn.Conv1d(n_in + 1, conv_channels, kernel_size=5, padding=2)      # :24
         else:
             self.pos_emb = None
@@ -151,7 +158,10 @@ class ConvModel(nn.Module):
         self._packed_versions = None
 
     def _geometry(self):
-        return self.n_in, self.conv_channels, 1 if self.pos_emb is not None else 0
+        # C-ABI `pos_emb`: 0 = off, 1 = on with max_len 100 (the reference), n > 1 = on with max_len n
+        if self.pos_emb is None:
+            return self.n_in, self.conv_channels, 0
+        return self.n_in, self.conv_channels, (1 if self.pos_emb.max_len == 100 else int(self.pos_emb.max_len))
 
     def packed_weights(self, fresh_from_kernel=False):
         """Extension-owned operand layouts (fp32 tap-major + bf16 UMMA blocks), rebuilt lazily when any
@@ -189,7 +199,7 @@ class ConvModel(nn.Module):
         if K * D != self.n_in:
             # the reference fails inside conv1 with a channel-mismatch RuntimeError
             raise RuntimeError(f"expected input with {self.n_in} channels (K*2), got {K * D} channels instead")
-        if self.pos_emb is not None and T != self.pos_emb.max_len:
+        if self.pos_emb is not None and T != self.pos_emb.max_len and not self.pos_emb_any_length:
             # torch.cat in LinearPositionalEmbedding.forward fails unless T == max_len (HandPoseModels.py:82)
             raise RuntimeError(f"Sizes of tensors must match: pos_emb requires T == {self.pos_emb.max_len}, got {T}")
         if inp.dtype not in (torch.float32, torch.bfloat16):
@@ -266,7 +276,7 @@ class ConvModel(nn.Module):
             raise RuntimeError(f"expected frames (F, {self.n_in // 2}, 2), got {tuple(frames.shape)}")
         if frames.dtype not in (torch.float32, torch.bfloat16):
             raise RuntimeError(f"frames must be float32 or bfloat16, got {frames.dtype}")
-        if self.pos_emb is not None and T != self.pos_emb.max_len:
+        if self.pos_emb is not None and T != self.pos_emb.max_len and not self.pos_emb_any_length:
             raise RuntimeError(f"Sizes of tensors must match: pos_emb requires T == {self.pos_emb.max_len}, got {T}")
         dev = frames.device
         x = frames.contiguous()

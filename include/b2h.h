@@ -53,7 +53,10 @@ int b2h_device_ok(void);
 /* ---- model geometry ------------------------------------------------------------------------
  * ConvModel.__init__  body2hand/src/models/HandPoseModels.py:18-37:
  * conv1 (C, n_in[+1 if pos_emb], 5), conv2/3 (C, C, 5), conv4 (42, C, 5) + biases; the flat fp32
- * parameter buffer holds them in state_dict order conv1.weight, conv1.bias, ..., conv4.bias. */
+ * parameter buffer holds them in state_dict order conv1.weight, conv1.bias, ..., conv4.bias.
+ * `pos_emb` everywhere in this ABI: 0 = off; 1 = LinearPositionalEmbedding with the reference's max_len = 100 (row t/100,
+ * models/HandPoseModels.py:23, 66-84); n > 1 = the same row with max_len = n (windows other than 100 frames --
+ * the reference's torch.cat only works for T == max_len, the kernels generate t/max_len for any T). */
 int64_t b2h_param_count(int n_in, int C, int pos_emb);
 /* float offset of conv{layer}.weight (is_bias=0) / .bias (is_bias=1) in the flat buffer, layer 1..4 */
 int64_t b2h_param_offset(int n_in, int C, int pos_emb, int layer, int is_bias);
@@ -103,6 +106,10 @@ int b2h_preprocess(const float* pose25, const float* hand_left, const float* han
                    const int64_t* win_start, const int64_t* win_end, int n_win, int T, int pad_mode, float factor, int dif_encoding,
                    int normalize, float* input_kp, float* input_conf, float* target_kp, float* target_conf,
                    float* left_kp, float* left_conf, int64_t* n_frames_out, void* input_kp_bf16, void* stream);
+
+/* 0 = clean, 1 = a preprocessing launch gave up waiting for a staged frame group (bounded spin, ~2 s): its outputs are
+ * incomplete.  Reading clears it.  Synchronises the device. */
+int b2h_preprocess_status(void);
 
 /* Test aid for the kernel's division: counts, over ALL 2^32 float bit patterns x, the cases where the
  * reciprocal+FMA division used for `factor` differs from IEEE div.rn(x, factor) (must be 0; mismatches_dev is a

@@ -7,7 +7,7 @@ import torch
 import b2h_oracle as oracle
 import hand_pose_sl_b200 as b2h
 from conftest import load_golden
-from hand_pose_sl_b200 import synthetic
+from hand_pose_sl_b200 import _lib, synthetic
 
 pytestmark = pytest.mark.gpu
 KEYS = ("input_kp", "input_conf", "target_kp", "target_conf", "left_hand_kp", "left_hand_conf", "n_frames")
@@ -115,3 +115,10 @@ def test_fast_division_is_exact_for_all_floats():
     _lib.check(lib.b2h_verify_fastdiv(1280.0, _lib.ptr(bad), _lib.stream_ptr()))
     torch.cuda.synchronize()
     assert int(bad.item()) == 0
+
+
+def test_preprocess_status_word_is_clean_after_the_suite():
+    """The staged-group wait of K0 is a bounded spin that records a timeout instead of breaking silently."""
+    import torch
+    torch.cuda.synchronize()
+    assert _lib.load().b2h_preprocess_status() == 0

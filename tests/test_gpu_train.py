@@ -479,3 +479,45 @@ def test_wide_training_fused_steps_follow_the_oracle():
         r.replay()
     r.finish()
     assert torch.equal(m2.flat_parameters(), m.flat_parameters())
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("T,max_len", [(64, 100), (200, 100), (37, 37), (128, 250)])
+def test_positional_embedding_beyond_100_frames(T, max_len, prec):
+    """the positional row t / max_len for windows other than 100 frames (the reference's torch.cat only
+    works for T == max_len).  Oracle = the reference formulas with the row built for the actual T: forward, loss and
+    gradients (conv1 has 25 input channels, the row is channel 0)."""
+    import torch.nn.functional as F
+    B = 4
+    sd = oracle.init_params(30, True, seed=T)
+    batch = synthetic.model_batch(B, T, seed=3 * T, ragged=True, len_seed=T)
+    m = b2h.ConvModel(30, "ReLU", True, precision=prec, pos_emb_max_len=max_len, pos_emb_any_length=True)
+    m.load_state_dict(sd)
+    m = m.to(DEV)
+    db = {k: (v.to(DEV) if k != "n_frames" else v) for k, v in batch.items()}
+    loss, grads, pred = b2h.forward_backward(m, db, want_pred=True)
+    torch.cuda.synchronize()
+    assert _lib.load().b2h_tc_status() == 0
+    # reference formulas (HandPoseModels.py:40-84) with pe = arange(T) / max_len
+    ps = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x = batch["input_kp"].reshape(B, T, 24).permute(0, 2, 1)
+    pe = (torch.arange(T).float() / max_len)[None, None, :].repeat(B, 1, 1)
+    h = torch.cat([pe, x], dim=1)
+    for l in range(1, 5):
+        h = F.conv1d(h, ps[f"conv{l}.weight"], ps[f"conv{l}.bias"], padding=2)
+        if l < 4:
+            h = F.relu(h)
+    out = h.view(B, 21, 2, T).permute(0, 3, 1, 2).contiguous()
+    out = oracle.mask_output(out, batch["n_frames"])
+    ref_loss = oracle.masked_pose_l1(out, batch["target_kp"], batch["n_frames"])
+    ref_loss.backward()
+    assert abs(float(loss) - float(ref_loss)) <= TOL[prec] * abs(float(ref_loss))
+    assert oracle.rel_err(pred.cpu().numpy(), out.detach().numpy()) <= TOL[prec]
+    if prec == "fp32":
+        for k, v in _split(m, grads).items():
+            assert oracle.rel_err(v, ps[k].grad.numpy()) <= GTOL[prec], k
+    # the reference behaviour is kept unless asked otherwise
+    strict = b2h.ConvModel(30, "ReLU", True, precision=prec).to(DEV)
+    if T != 100:
+        with pytest.raises(RuntimeError):
+            strict(db["input_kp"])
