@@ -207,49 +207,67 @@ class TrainStepRunner(_StepBuffers):
         return self.loss[slot]
 
 
-def pipelined_steps(runner, batches, status_every=0):
+def pipelined_steps(runner, batches, status_every=0, copy_streams=2):
     """Training loop with a double-buffered input pipeline (what a DataLoader with prefetch gives the reference loop,
-    steps/traintest.py:87-123): while step i runs, batch i+1 travels host -> device on a copy stream into the other
+    steps/traintest.py:87-123): while step i runs, batch i+1 travels host -> device on copy stream(s) into the other
     slot.  `runner` is a TrainStepRunner or parallel.DataParallelTrainer with n_slots >= 2; `batches` yields either
-    `runner.host_stage(...)` buffers (ONE copy per step) or reference-style batch dicts in pinned host memory.
-    Yields the loss of every step as a float (device -> host read, traintest.py:123), so each step's result is
-    observed before the next one is enqueued."""
+    `runner.host_stage(...)` buffers or reference-style batch dicts in pinned host memory.  A staged buffer is moved as
+    `copy_streams` contiguous pieces on as many streams (measured on B200: one 3.5 MB pinned copy 42 GB/s, two halves in
+    parallel 49 GB/s).  Yields the loss of every step as a float (device -> host read through a pinned word,
+    traintest.py:123), so each step's result is observed before the next one is enqueued."""
     if runner.n_slots < 2:
         raise RuntimeError("pipelined_steps needs a runner with n_slots >= 2")
     dev = runner.x.device
     main = torch.cuda.current_stream(dev)
-    copy_stream = torch.cuda.Stream(dev)
-    ready = [torch.cuda.Event(), torch.cuda.Event()]     # batch landed in slot s
-    freed = [torch.cuda.Event(), torch.cuda.Event()]     # the step that read slot s has finished
+    ncs = max(1, int(copy_streams))
+    cstreams = [torch.cuda.Stream(dev) for _ in range(ncs)]
+    ready = [[torch.cuda.Event() for _ in range(ncs)] for _ in range(2)]     # piece h of the batch landed in slot s
+    freed = [torch.cuda.Event(), torch.cuda.Event()]                         # the step that read slot s has finished
     used = [False, False]
     it = iter(batches)
+    host_loss = None
 
     def issue(i, batch):
         s = i & 1
-        if used[s]:
-            copy_stream.wait_event(freed[s])             # do not overwrite a slot a step is still reading
-        with torch.cuda.stream(copy_stream):
-            if isinstance(batch, torch.Tensor):
-                runner.load_staged(batch, slot=s)
-            else:
-                runner.load(batch, slot=s)
-            ready[s].record(copy_stream)
+        staged = isinstance(batch, torch.Tensor)
+        k = ncs if staged else 1
+        n = batch.numel() if staged else 0
+        for h in range(k):
+            cs = cstreams[h]
+            if used[s]:
+                cs.wait_event(freed[s])                  # do not overwrite a slot a step is still reading
+            with torch.cuda.stream(cs):
+                if staged:
+                    lo, hi = n * h // k // 256 * 256, (n * (h + 1) // k // 256 * 256 if h + 1 < k else n)
+                    runner.stage[s][lo:hi].copy_(batch[lo:hi], non_blocking=True)
+                else:
+                    runner.load(batch, slot=s)
+                ready[s][h].record(cs)
+        return k
 
     nxt = next(it, None)
     if nxt is None:
         return
-    issue(0, nxt)
+    pieces = {0: issue(0, nxt)}
     i = 0
     while True:
         s = i & 1
         nxt = next(it, None)
         if nxt is not None:
-            issue(i + 1, nxt)                            # travels while step i computes
-        main.wait_event(ready[s])
+            pieces[(i + 1) & 1] = issue(i + 1, nxt)      # travels while step i computes
+        for h in range(pieces[s]):
+            main.wait_event(ready[s][h])
         loss = runner.step(s)
         freed[s].record(main)
         used[s] = True
-        yield float(loss.item())
+        if loss.is_cuda:
+            if host_loss is None:
+                host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+            host_loss.copy_(loss.reshape(1), non_blocking=True)
+            main.synchronize()
+            yield float(host_loss[0])
+        else:
+            yield float(loss.item())
         if status_every and (i + 1) % status_every == 0:
             runner.check_status()
         if nxt is None:

@@ -42,3 +42,25 @@ wr.x[0].copy_(synthetic.model_batch(1184, 126, seed=300)["input_kp"])
 for _ in range(reps):
     wr.run(0)
 torch.cuda.synchronize()
+
+# fp32 mode on the tensor pipe (bf16 high/low operand pairs): forward B=512 and the fused train step B=256
+f32 = b2h.ConvModel(30, "ReLU", False, precision="fp32").to(dev)
+fr32 = ForwardRunner(f32, 512, 64)
+fr32.x[0].copy_(synthetic.model_batch(512, 64, seed=99)["input_kp"])
+o32 = b2h.FusedAdam(f32.parameters(), lr=2e-4)
+r32 = TrainStepRunner(f32, o32, 256, 64)
+r32.load(synthetic.model_batch(256, 64, seed=1234), non_blocking=False)
+for _ in range(reps):
+    fr32.run(0)
+    r32.step(0)
+torch.cuda.synchronize()
+
+# wide training (conv_channels = 256, batch 256 x 64): forward+criterion / dgrad chain / split-K wgrad / Adam
+wt = b2h.ConvModel(256, "ReLU", False, precision="bf16").to(dev)
+wo = b2h.FusedAdam(wt.parameters(), lr=2e-4)
+wr2 = TrainStepRunner(wt, wo, 256, 64)
+wr2.load(synthetic.model_batch(256, 64, seed=5), non_blocking=False)
+for _ in range(reps):
+    wr2.step(0)
+torch.cuda.synchronize()
+print("prof_target: fp32 loss", float(r32.loss[0]), "wide loss", float(wr2.loss[0]))
