@@ -122,11 +122,19 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
   loss_partial_sum(a.loss_partials, a.n_loss_parts, a.loss_out);
 }
 
-// Large models (wide training: P ~ 740k, a handful of split-K slices): one thread per gradient-partial slot, coalesced
-// loads of the slot from every slice (fixed order -> deterministic), Adam, scatter into the packed operand layouts.
-// (adam_kernel's 32-slots-per-block shape is built for ~20k slots x 128 slices; at 760k slots its 24k blocks cost 400 us.)
-__global__ void __launch_bounds__(256) adam_gp_wide_kernel(AdamArgs a) {
+// Few gradient slices (wide training: split-K factor 6..37; small batches of the tile kernel): Adam with BOTH sides coalesced.
+// The gradient slices are in slot order [k][ci/4][co][4] (what the TMEM read-out writes), the parameters / moments in the
+// reference's (co, ci, k) order: one thread per slot made every m / v / p access and most packed-operand stores hit their
+// own 32-byte sector (ncu at C = 256: 302 MB of DRAM writes for 3 MB of parameters, 87 us).  Here a block owns 4 output
+// channels of one layer: (1) sum the slices in slot order (64-B runs) into shared memory [co][ci][k], (2) walk the flat
+// order -- cin*5 contiguous floats per output channel -- for the Adam update, (3) scatter the new weights into the packed
+// operand layouts in slot order, where their stores coalesce.  Fixed summation order -> deterministic.
+constexpr int kAdamCoGroup = 4;
+__global__ void __launch_bounds__(256) adam_gp_tile_kernel(AdamArgs a) {
+  extern __shared__ float g_s[];                      // [kAdamCoGroup][kp][5] gradient sums, then the new weights
   __shared__ float s_step_size, s_inv_bc2_sqrt;
+  __shared__ float b_s[kAdamCoGroup];
+  const Geo& g = a.g;
   if (a.step_dev || a.lr_dev) {
     if (threadIdx.x == 0) {
       const long long t = a.step_dev ? *a.step_dev : a.step_host;
@@ -134,26 +142,80 @@ __global__ void __launch_bounds__(256) adam_gp_wide_kernel(AdamArgs a) {
       s_step_size = (float)(lr / (1.0 - ipow(a.beta1_d, t)));
       s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - ipow(a.beta2_d, t)));
     }
-    __syncthreads();
-    a.step_size = s_step_size;
-    a.inv_bc2_sqrt = s_inv_bc2_sqrt;
+  } else if (threadIdx.x == 0) {
+    s_step_size = a.step_size; s_inv_bc2_sqrt = a.inv_bc2_sqrt;
   }
-  const int nj = gp_total(a.g);
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < nj) {
-    float gr = 0.f;
-    for (int c = 0; c < a.nparts; ++c) gr += __ldcs(a.grads + (size_t)c * nj + j);
-    GpSlot sl;
-    if (gp_decode(a.g, j, sl)) {
-      const int i = gp_flat_of_slot(a.g, sl);
-      gr *= a.grad_scale;
-      float m = a.m[i], v = a.v[i], p = a.params[i];
-      m = fmaf(gr - m, a.one_minus_b1, m);
-      v = fmaf(a.one_minus_b2 * gr, gr, v * a.beta2);
-      const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
-      p = p - a.step_size * (m / denom);
-      a.m[i] = m; a.v[i] = v; a.params[i] = p;
-      if (a.packed) scatter_packed_slot(a.g, a.packed, sl, p);
+  // block -> (layer, first output channel)
+  int l = 0, b = blockIdx.x;
+  for (int q = 0; q < 4; ++q) {
+    const int nb = (g.cout[q] + kAdamCoGroup - 1) / kAdamCoGroup;
+    if (b >= nb && q < 3) { b -= nb; l = q + 1; } else break;
+  }
+  const int co0 = b * kAdamCoGroup;
+  const int kp = g.kp[l], cin = g.cin[l], cout = g.cout[l], q4 = kp >> 2;
+  const int nj = gp_total(g);
+  const size_t base = (size_t)gp_layer_off(g, l);
+  const int nslot = B2H_KW * q4 * kAdamCoGroup * 4;
+  // (1) slot order: idx = ((k * q4 + q) * 4 + cl) * 4 + e  ->  64-byte runs of the slices
+  for (int idx = threadIdx.x; idx < nslot; idx += blockDim.x) {
+    const int e = idx & 3, cl = (idx >> 2) & (kAdamCoGroup - 1), r = idx >> 4;
+    const int q = r % q4, k = r / q4;
+    const int co = co0 + cl;
+    float s = 0.f;
+    if (co < cout) {
+      const size_t j = base + ((size_t)(k * q4 + q) * cout + co) * 4 + e;
+      for (int c = 0; c < a.nparts; ++c) s += __ldcs(a.grads + (size_t)c * nj + j);
+    }
+    g_s[(cl * kp + 4 * q + e) * B2H_KW + k] = s;
+  }
+  if (threadIdx.x < kAdamCoGroup) {
+    const int co = co0 + threadIdx.x;
+    float s = 0.f;
+    if (co < cout) {
+      const size_t j = base + (size_t)B2H_KW * cout * kp + co;
+      for (int c = 0; c < a.nparts; ++c) s += __ldcs(a.grads + (size_t)c * nj + j);
+    }
+    b_s[threadIdx.x] = s;
+  }
+  __syncthreads();
+  const float step_size = s_step_size, inv_bc2_sqrt = s_inv_bc2_sqrt;
+  auto adam1 = [&](int i, float gr) {
+    gr *= a.grad_scale;
+    float m = a.m[i], v = a.v[i], p = a.params[i];
+    m = fmaf(gr - m, a.one_minus_b1, m);
+    v = fmaf(a.one_minus_b2 * gr, gr, v * a.beta2);
+    const float denom = sqrtf(v) * inv_bc2_sqrt + a.eps;
+    p = p - step_size * (m / denom);
+    a.m[i] = m; a.v[i] = v; a.params[i] = p;
+    return p;
+  };
+  // (2) flat order: the cin*5 weights of one output channel are contiguous
+  for (int cl = 0; cl < kAdamCoGroup; ++cl) {
+    const int co = co0 + cl;
+    if (co >= cout) break;
+    const int i0 = g.w_off[l] + co * cin * B2H_KW;
+    for (int r = threadIdx.x; r < cin * B2H_KW; r += blockDim.x) {
+      const int ci = r / B2H_KW, k = r - ci * B2H_KW;
+      float* gs = &g_s[(cl * kp + ci) * B2H_KW + k];
+      *gs = adam1(i0 + r, *gs);
+    }
+  }
+  if (threadIdx.x < kAdamCoGroup && co0 + (int)threadIdx.x < cout) {
+    const int co = co0 + threadIdx.x;
+    const float p = adam1(g.b_off[l] + co, b_s[threadIdx.x]);
+    if (a.packed && co < 64) reinterpret_cast<float*>(a.packed + g.bias_off)[l * 64 + co] = p;
+  }
+  __syncthreads();
+  // (3) slot order again: scatter the new weights into the packed operand layouts
+  if (a.packed) {
+    for (int idx = threadIdx.x; idx < nslot; idx += blockDim.x) {
+      const int e = idx & 3, cl = (idx >> 2) & (kAdamCoGroup - 1), r = idx >> 4;
+      const int q = r % q4, k = r / q4;
+      const int co = co0 + cl, ci = 4 * q + e;
+      if (co < cout && ci < cin) {
+        GpSlot sl; sl.l = l; sl.k = k; sl.co = co; sl.ci = ci; sl.is_bias = false;
+        scatter_packed_slot(g, a.packed, sl, g_s[(cl * kp + ci) * B2H_KW + k]);
+      }
     }
   }
   loss_partial_sum(a.loss_partials, a.n_loss_parts, a.loss_out);
@@ -428,10 +490,13 @@ int launch_adam(float* params, const float* grads, int nparts, int gp_layout, fl
   a.loss_partials = loss_partials; a.loss_out = loss_out;
   a.lr_d = lr; a.beta1_d = beta1; a.beta2_d = beta2; a.step_dev = step_dev; a.lr_dev = lr_dev; a.step_host = step;
   const int64_t nj = gp_layout ? (int64_t)gp_total(g) : n;
-  if (gp_layout && nparts <= 64) {                     // few slices (wide training, small batches): one thread per slot
-    adam_gp_wide_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, stream>>>(a);
+  if (gp_layout && nparts <= 64) {                     // few slices (wide training, small batches): coalesced on both sides
+    int blocks = 0, kpmax = 0;
+    for (int l = 0; l < 4; ++l) { blocks += (g.cout[l] + kAdamCoGroup - 1) / kAdamCoGroup; kpmax = g.kp[l] > kpmax ? g.kp[l] : kpmax; }
+    const size_t smem = (size_t)kAdamCoGroup * kpmax * B2H_KW * sizeof(float);
+    adam_gp_tile_kernel<<<blocks, 256, smem, stream>>>(a);
     count_launch();
-    return check_launch("adam_gp_wide_kernel");
+    return check_launch("adam_gp_tile_kernel");
   }
   if (nparts == 1) adam_kernel<<<(unsigned)((nj + 31) / 32), 32, 0, stream>>>(a);
   else adam_kernel<<<(unsigned)((nj + 31) / 32), 256, 0, stream>>>(a);
