@@ -221,6 +221,43 @@ __global__ void __launch_bounds__(256) adam_gp_tile_kernel(AdamArgs a) {
   loss_partial_sum(a.loss_partials, a.n_loss_parts, a.loss_out);
 }
 
+// Few slices, small model (conv_channels ~ 64): one thread per gradient-partial slot, coalesced loads of the slot from every
+// slice (fixed order -> deterministic), Adam, scatter into the packed operand layouts.  (adam_kernel's 32-slots-per-block
+// shape is built for ~20k slots x 128 slices; adam_gp_tile_kernel needs >= ~100 blocks of work to fill the chip.)
+__global__ void __launch_bounds__(256) adam_gp_wide_kernel(AdamArgs a) {
+  __shared__ float s_step_size, s_inv_bc2_sqrt;
+  if (a.step_dev || a.lr_dev) {
+    if (threadIdx.x == 0) {
+      const long long t = a.step_dev ? *a.step_dev : a.step_host;
+      const double lr = a.lr_dev ? *a.lr_dev : a.lr_d;
+      s_step_size = (float)(lr / (1.0 - ipow(a.beta1_d, t)));
+      s_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - ipow(a.beta2_d, t)));
+    }
+    __syncthreads();
+    a.step_size = s_step_size;
+    a.inv_bc2_sqrt = s_inv_bc2_sqrt;
+  }
+  const int nj = gp_total(a.g);
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nj) {
+    float gr = 0.f;
+    for (int c = 0; c < a.nparts; ++c) gr += __ldcs(a.grads + (size_t)c * nj + j);
+    GpSlot sl;
+    if (gp_decode(a.g, j, sl)) {
+      const int i = gp_flat_of_slot(a.g, sl);
+      gr *= a.grad_scale;
+      float m = a.m[i], v = a.v[i], p = a.params[i];
+      m = fmaf(gr - m, a.one_minus_b1, m);
+      v = fmaf(a.one_minus_b2 * gr, gr, v * a.beta2);
+      const float denom = sqrtf(v) * a.inv_bc2_sqrt + a.eps;
+      p = p - a.step_size * (m / denom);
+      a.m[i] = m; a.v[i] = v; a.params[i] = p;
+      if (a.packed) scatter_packed_slot(a.g, a.packed, sl, p);
+    }
+  }
+  loss_partial_sum(a.loss_partials, a.n_loss_parts, a.loss_out);
+}
+
 // grads[i] = sum_c partials[c][slot(i)] for the same shape of problem (one thread per slot)
 __global__ void __launch_bounds__(256) reduce_gp_wide_kernel(const float* __restrict__ partials, int nparts, Geo g, float* __restrict__ grads,
                                                              const float* __restrict__ loss_partials, float* __restrict__ loss_out,
@@ -490,7 +527,12 @@ int launch_adam(float* params, const float* grads, int nparts, int gp_layout, fl
   a.loss_partials = loss_partials; a.loss_out = loss_out;
   a.lr_d = lr; a.beta1_d = beta1; a.beta2_d = beta2; a.step_dev = step_dev; a.lr_dev = lr_dev; a.step_host = step;
   const int64_t nj = gp_layout ? (int64_t)gp_total(g) : n;
-  if (gp_layout && nparts <= 64) {                     // few slices (wide training, small batches): coalesced on both sides
+  if (gp_layout && nparts <= 64 && nj <= 100000) {     // few slices, small model: one thread per slot
+    adam_gp_wide_kernel<<<(unsigned)((nj + 255) / 256), 256, 0, stream>>>(a);
+    count_launch();
+    return check_launch("adam_gp_wide_kernel");
+  }
+  if (gp_layout && nparts <= 64) {                     // few slices, large model (wide training): coalesced on both sides
     int blocks = 0, kpmax = 0;
     for (int l = 0; l < 4; ++l) { blocks += (g.cout[l] + kAdamCoGroup - 1) / kAdamCoGroup; kpmax = g.kp[l] > kpmax ? g.kp[l] : kpmax; }
     const size_t smem = (size_t)kAdamCoGroup * kpmax * B2H_KW * sizeof(float);
