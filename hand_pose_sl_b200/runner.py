@@ -207,14 +207,15 @@ class TrainStepRunner(_StepBuffers):
         return self.loss[slot]
 
 
-def pipelined_steps(runner, batches, status_every=0, copy_streams=2):
+def pipelined_steps(runner, batches, status_every=0, copy_streams=1):
     """Training loop with a double-buffered input pipeline (what a DataLoader with prefetch gives the reference loop,
     steps/traintest.py:87-123): while step i runs, batch i+1 travels host -> device on copy stream(s) into the other
     slot.  `runner` is a TrainStepRunner or parallel.DataParallelTrainer with n_slots >= 2; `batches` yields either
-    `runner.host_stage(...)` buffers or reference-style batch dicts in pinned host memory.  A staged buffer is moved as
-    `copy_streams` contiguous pieces on as many streams (measured on B200: one 3.5 MB pinned copy 42 GB/s, two halves in
-    parallel 49 GB/s).  Yields the loss of every step as a float (device -> host read through a pinned word,
-    traintest.py:123), so each step's result is observed before the next one is enqueued."""
+    `runner.host_stage(...)` buffers or reference-style batch dicts in pinned host memory.  A staged buffer can be moved as
+    `copy_streams` contiguous pieces on as many streams: in isolation two halves in parallel reach 49 GB/s against
+    42 GB/s for one 3.5 MB copy on B200, but inside this loop the extra per-step host calls cost more than the copy
+    gains (150 -> 124 Mframes/s measured), so the default is one stream.  Yields the loss of every step as a float
+    (device -> host read, traintest.py:123), so each step's result is observed before the next one is enqueued."""
     if runner.n_slots < 2:
         raise RuntimeError("pipelined_steps needs a runner with n_slots >= 2")
     dev = runner.x.device
@@ -225,7 +226,6 @@ def pipelined_steps(runner, batches, status_every=0, copy_streams=2):
     freed = [torch.cuda.Event(), torch.cuda.Event()]                         # the step that read slot s has finished
     used = [False, False]
     it = iter(batches)
-    host_loss = None
 
     def issue(i, batch):
         s = i & 1
@@ -260,14 +260,7 @@ def pipelined_steps(runner, batches, status_every=0, copy_streams=2):
         loss = runner.step(s)
         freed[s].record(main)
         used[s] = True
-        if loss.is_cuda:
-            if host_loss is None:
-                host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
-            host_loss.copy_(loss.reshape(1), non_blocking=True)
-            main.synchronize()
-            yield float(host_loss[0])
-        else:
-            yield float(loss.item())
+        yield float(loss.item())
         if status_every and (i + 1) % status_every == 0:
             runner.check_status()
         if nxt is None:

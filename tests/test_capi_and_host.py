@@ -236,10 +236,9 @@ def test_pipelined_steps_slot_discipline(monkeypatch):
     assert [(b, s) for _, b, s in loads] == [(0, 0), (1, 1), (2, 0), (3, 1), (4, 0)] and len(steps) == 5
     for i in range(4):       # load(i+1) precedes step(i)
         assert log.index(("load", i + 1, (i + 1) & 1)) < [k for k, e in enumerate(log) if e[0] == "step"][i]
-    # event ids in construction order: ready[slot][piece] = 1..4 (2 slots x 2 copy streams), freed[0], freed[1] = 5, 6;
-    # a batch dict (not a staged buffer) travels as ONE piece on the first copy stream
-    ready = {0: 1, 1: 3}
-    freed = {0: 5, 1: 6}
+    # event ids in construction order: ready[slot][piece] = 1, 2 (2 slots x 1 copy stream), freed[0], freed[1] = 3, 4
+    ready = {0: 1, 1: 2}
+    freed = {0: 3, 1: 4}
     for i in range(5):       # step i is preceded by main.wait(ready[slot]) and followed by record(freed[slot])
         k = [k for k, e in enumerate(log) if e[0] == "step"][i]
         assert log[k - 1] == ("wait", "main", ready[i & 1]) and log[k + 1] == ("record", freed[i & 1], "main")
