@@ -123,26 +123,27 @@ class DataParallelTrainer(_StepBuffers):
                 import warnings
                 warnings.warn(f"symmetric-memory gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
 
-    def step(self, slot=0):
+    def step(self, slot=0, to_host=False):
         self._sync_host_state()
         m, g = self.model, self.opt.param_groups[0]
         n_in, C, pe = m._geometry()
         b1, b2 = g["betas"]
         conf = None if self.conf is None else self.conf[slot]
         sp = _lib.stream_ptr(self.dev)
+        loss = (self.loss_host if to_host else self.loss)[slot:slot + 1]
         if self.exchange == "p2p":
             _lib.check(self.lib.b2h_train_step_dp(
                 _lib.ptr(self.x[slot]), self._x_dt(), _lib.ptr(self.target[slot]), _lib.ptr(conf), _lib.ptr(self.lengths[slot]),
                 _lib.ptr(m._flat), _lib.ptr(self.packed), _lib.ptr(self.state["m"]), _lib.ptr(self.state["v"]),
-                _lib.ptr(self.loss[slot:slot + 1]), self.B, self.T, n_in, C, pe, self.kind, _lib.PRECISIONS[m.precision],
+                _lib.ptr(loss), self.B, self.T, n_in, C, pe, self.kind, _lib.PRECISIONS[m.precision],
                 float(g["lr"]), b1, b2, g["eps"], _lib.ptr(self.step_dev), _lib.ptr(self.epoch_dev), _lib.ptr(self.lr_dev),
                 _lib.ptr(self.sym), _lib.ptr(self.peer_ptrs), (self.mc_ptr or None), self.rank, self.world,
                 grad_scale_for(self.loss_name, self.world), _lib.ptr(self.ws), self.ws.numel(), sp))
             self._advance(1)
-            return self.loss[slot]
+            return loss[0]
         _lib.check(self.lib.b2h_train_forward_backward(
             _lib.ptr(self.x[slot]), self._x_dt(), _lib.ptr(self.target[slot]), _lib.ptr(conf), _lib.ptr(self.lengths[slot]),
-            _lib.ptr(m._flat), _lib.ptr(self.packed), _lib.ptr(self.grads), _lib.ptr(self.loss[slot:slot + 1]), None,
+            _lib.ptr(m._flat), _lib.ptr(self.packed), _lib.ptr(self.grads), _lib.ptr(loss), None,
             self.B, self.T, n_in, C, pe, self.kind, _lib.PRECISIONS[m.precision], _lib.ptr(self.step_dev),
             _lib.ptr(self.ws), self.ws.numel(), sp))
         allreduce_flat(self.grads, self.group)
@@ -151,7 +152,7 @@ class DataParallelTrainer(_StepBuffers):
             float(g["lr"]), b1, b2, g["eps"], 0, _lib.ptr(self.step_dev), _lib.ptr(self.lr_dev),
             grad_scale_for(self.loss_name, self.world), _lib.ptr(self.packed), n_in, C, pe, sp))
         self._advance(1)
-        return self.loss[slot]
+        return loss[0]
 
     def replica_checksum(self):
         """(sum, sum of squares) of the flat parameters in float64 -- equal on every rank iff the replicas are

@@ -390,6 +390,16 @@ def test_staged_single_copy_inputs_are_bit_identical():
         r.finish()
         out.append((losses, m.flat_parameters().clone()))
     assert out[0][0] == out[1][0] and torch.equal(out[0][1], out[1][1])
+    # the loss written straight into pinned host memory by the kernel (to_host=True) == the device-side loss, and the
+    # pipelined loop that uses it yields the same trajectory
+    from hand_pose_sl_b200.runner import pipelined_steps
+    m = _model(sd, 30, False, "bf16")
+    opt = b2h.FusedAdam(m.parameters(), lr=2e-4)
+    r = TrainStepRunner(m, opt, 32, 64, "confL1", n_slots=2, x_dtype=torch.bfloat16)
+    st = r.host_stage(batch)
+    piped = list(pipelined_steps(r, [st, st, st]))
+    r.finish()
+    assert piped == out[1][0] and torch.equal(m.flat_parameters(), out[1][1])
 
 
 def test_fp32_mode_split_kernel_matches_ffma_arbiter():
