@@ -297,7 +297,7 @@ def main():
 
     # ---------------- e2e: pinned host buffer -> ONE H2D copy -> step -> D2H loss, every step ----------------
     # runner.pipelined_steps: batch i+1 travels on a copy stream while step i computes (what a prefetching DataLoader
-    # gives the reference loop); the loss of every step is read back on the host before the next step is enqueued.
+    # gives the reference loop); the loss of every step is read on the host inside the loop (one step behind the launch).
     from hand_pose_sl_b200.runner import pipelined_steps
     e2e_steps = 200
     h2d = int(staged[0].numel())
@@ -326,7 +326,8 @@ def main():
         e2e_dt, seq_dt = float(t[0].item()), float(t[1].item())
     e2e = {"value": n_p * B_TRAIN * T * world / e2e_dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": 4, "steps": n_p,
-           "api": "runner.pipelined_steps(runner, runner.host_stage(batch) buffers): ONE cudaMemcpyAsync + step + loss.item() per step",
+           "api": "runner.pipelined_steps(runner, runner.host_stage(batch) buffers): per step ONE cudaMemcpyAsync of the pinned batch, "
+                  "the step, and the loss read on the host (the kernel stores it into pinned host memory; read one step behind the launch)",
            "mode": "pipelined (double-buffered H2D on a copy stream)", "input_dtype": str(x_dt).replace("torch.", ""),
            "sequential_value": B_TRAIN * T * world / seq_dt, "us_per_step": e2e_dt / max(n_p, 1) * 1e6,
            "h2d_gbs": h2d / (e2e_dt / max(n_p, 1)) / 1e9}
