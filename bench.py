@@ -467,6 +467,8 @@ def main():
                             ("train_fp32_ffma", lambda: time_train("fp32-ffma", B_TRAIN, T)),
                             ("fwd_fp32_ffma", lambda: time_fwd("fp32-ffma", B_FWD, T)),
                             ("train_wide", lambda: time_train("bf16", B_TRAIN, T, Cx=256, slots=4, reps=5)),
+                            ("train_wide_b444", lambda: time_train("bf16", 444, T, Cx=256, slots=2, reps=5)),     # 148 tiles: one per SM
+                            ("train_wide_b888", lambda: time_train("bf16", 888, T, Cx=256, slots=2, reps=5)),
                             ("train_wide_c128", lambda: time_train("bf16", B_TRAIN, T, Cx=128, slots=4, reps=5)),
                             ("train_c64", lambda: time_train("bf16", B_TRAIN, T, Cx=64, slots=4, reps=5)),
                             ("train_ref_default_shape", lambda: time_train(train_prec, 128, 200)),

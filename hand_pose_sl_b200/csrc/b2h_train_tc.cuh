@@ -892,7 +892,9 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           float gr = 0.f;
           for (int pg = 0; pg < groups; ++pg) gr += red[(size_t)pg * ncol * 4 + (j - jb)];
           bool apply = true;
-          if (dp) {
+          // padding slots of the slot layout (ci >= cin, bias pad: ~10 % at C = 30) carry no parameter: neither pushed nor polled
+          const bool real_slot = one_pass ? (my_i >= 0) : (flat_index_of_gp(g, j) >= 0);
+          if (dp && real_slot) {
             // push my slot to every rank, then collect the world's slots for the same j from my own buffer and sum them
             // in rank order (identical arithmetic on every rank).  With a multicast (NVLS) mapping of the exchange
             // buffers ONE multimem.st is replicated by the NVSwitch into every rank's buffer; otherwise W unicast
