@@ -201,6 +201,22 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_kernel(WideArgs 
           act_phase ^= 1;
           tc_fence_after();
           if (p.dbg && blockIdx.x == 0 && dn < 8) p.dbg[dn++] = clock64();   // layer inputs ready
+          if (MODE != 0) {
+            // Training: the buffer now holds this stage's INPUT, which the weight-gradient GEMM needs later: dump it to the
+            // tile's scratch with asynchronous bulk stores (TMA engine) that run under this stage's MMAs.  MODE 1: ACT[l]
+            // (x, a1, a2, a3).  MODE 2: the input of stage j > 0 is the previous stage's output dZ -> DZ[layer] (DZ[3] was
+            // written by the forward's criterion epilogue; the last stage's output DZ[0] is stored by its epilogue threads).
+            // The epilogue threads ran fence.proxy.async before arriving on act_ready.
+            const int nch = MODE == 1 ? g.kp[l] / 8 : g.np_[p.st[l].layer] / 8;
+            if (MODE == 1 || l > 0) {
+              unsigned char* dst = p.scratch + (size_t)tile * p.tile_bytes + (MODE == 1 ? p.act_off[l] : p.dz_off[p.st[l].layer]);
+              for (int c = 0; c < nch; c += 4) {
+                const int n = nch - c < 4 ? nch - c : 4;
+                bulk_s2g(dst + (size_t)c * CH, A + (size_t)c * CH, (uint32_t)n * CH);
+              }
+              bulk_commit();
+            }
+          }
           int s = 0, left = sc.nblk;
           uint32_t a_tap = a_lo0, a_cur = a_lo0;       // output row 2+m reads input row m+k: tap k = +k rows
           uint32_t acc = 0;
@@ -222,9 +238,11 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_kernel(WideArgs 
             commit_addr(empty0 + slot * 8);            // stage reusable once these MMAs have read it
             if (++slot == (uint32_t)S) { slot = 0; ph ^= 1; }
           }
+          if (MODE != 0) bulk_wait_read0();            // the dump has read the buffer: the epilogue may overwrite it in place
           commit_addr(acc_addr);
           if (p.dbg && blockIdx.x == 0 && dn < 8) p.dbg[dn++] = clock64();   // layer MMAs issued
         }
+      if (MODE != 0) bulk_wait0();                     // every dump has reached global memory before the CTA retires
     }
     __syncwarp();
   } else {
@@ -266,8 +284,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_kernel(WideArgs 
         for (int i = tid; i < nch * rows; i += kWideEpiThreads) dst[i] = src[i];
         return;
       }
-      unsigned char* d0 = (MODE == 1 && tile < p.n_tiles) ? dump(tile, p.act_off[0]) : nullptr;
-      if (d0) zero_halo(d0, nch0);
+      unsigned char* d0 = nullptr;                   // (the input dump ACT[0] is a bulk store issued at the stage's start)
       for (int j = 0; j < 2; ++j) {
         const RowCtx rc = rowctx(j, tile);
         for (int c8 = ch; c8 < nch0; c8 += 2) {
@@ -371,8 +388,9 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_kernel(WideArgs 
           const uint32_t taddr = tbase + lane_addr;
           // MODE 1: a_{l+1} = input of layer l+1 -> ACT[l+1];  MODE 2: dZ_{layer-1} -> DZ[layer-1], masked by the saved
           // input of `layer` (= a_layer = relu output of layer-1)
-          unsigned char* dd = MODE == 1 ? dump(tile, p.act_off[l + 1]) : (MODE == 2 ? dump(tile, p.dz_off[layer - 1]) : nullptr);
-          if (MODE != 0) zero_halo(dd, N / 8);
+          // MODE 2, last stage: dZ_0 has no later stage whose start would dump it -> stored by these threads
+          unsigned char* dd = (MODE == 2 && l == NL - 1) ? dump(tile, p.dz_off[layer - 1]) : nullptr;
+          if (dd) zero_halo(dd, N / 8);
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int c0 = 32 * ch + 64 * it;
@@ -405,7 +423,7 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_kernel(WideArgs 
               const size_t o0 = (size_t)((c0 >> 3) + i) * CH + (size_t)rc0.row * 16, o1 = (size_t)((c0 >> 3) + i) * CH + (size_t)rc1.row * 16;
               *reinterpret_cast<uint4*>(A + o0) = q0;
               *reinterpret_cast<uint4*>(A + o1) = q1;
-              if (MODE != 0) {
+              if (dd) {
                 *reinterpret_cast<uint4*>(dd + o0) = q0;
                 *reinterpret_cast<uint4*>(dd + o1) = q1;
               }
