@@ -125,11 +125,11 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
 // Few gradient slices (wide training: split-K factor 6..37; small batches of the tile kernel): Adam with BOTH sides coalesced.
 // The gradient slices are in slot order [k][ci/4][co][4] (what the TMEM read-out writes), the parameters / moments in the
 // reference's (co, ci, k) order: one thread per slot made every m / v / p access and most packed-operand stores hit their
-// own 32-byte sector (ncu at C = 256: 302 MB of DRAM writes for 3 MB of parameters, 87 us).  Here a block owns 4 output
-// channels of one layer: (1) sum the slices in slot order (64-B runs) into shared memory [co][ci][k], (2) walk the flat
+// own 32-byte sector (ncu at C = 256: 302 MB of DRAM writes for 3 MB of parameters, 87 us).  Here a block owns 2 output
+// channels of one layer: (1) sum the slices in slot order (32-B runs) into shared memory [co][ci][k], (2) walk the flat
 // order -- cin*5 contiguous floats per output channel -- for the Adam update, (3) scatter the new weights into the packed
 // operand layouts in slot order, where their stores coalesce.  Fixed summation order -> deterministic.
-constexpr int kAdamCoGroup = 4;
+constexpr int kAdamCoGroup = 2;   // output channels per block: 406 blocks at C = 256 (latency-bound kernel: many small blocks)
 __global__ void __launch_bounds__(256) adam_gp_tile_kernel(AdamArgs a) {
   extern __shared__ float g_s[];                      // [kAdamCoGroup][kp][5] gradient sums, then the new weights
   __shared__ float s_step_size, s_inv_bc2_sqrt;
@@ -158,13 +158,19 @@ __global__ void __launch_bounds__(256) adam_gp_tile_kernel(AdamArgs a) {
   const int nslot = B2H_KW * q4 * kAdamCoGroup * 4;
   // (1) slot order: idx = ((k * q4 + q) * 4 + cl) * 4 + e  ->  64-byte runs of the slices
   for (int idx = threadIdx.x; idx < nslot; idx += blockDim.x) {
-    const int e = idx & 3, cl = (idx >> 2) & (kAdamCoGroup - 1), r = idx >> 4;
+    const int e = idx & 3, cl = (idx >> 2) % kAdamCoGroup, r = idx / (4 * kAdamCoGroup);
     const int q = r % q4, k = r / q4;
     const int co = co0 + cl;
     float s = 0.f;
     if (co < cout) {
-      const size_t j = base + ((size_t)(k * q4 + q) * cout + co) * 4 + e;
-      for (int c = 0; c < a.nparts; ++c) s += __ldcs(a.grads + (size_t)c * nj + j);
+      const float* src = a.grads + base + ((size_t)(k * q4 + q) * cout + co) * 4 + e;
+      for (int c0 = 0; c0 < a.nparts; c0 += 8) {         // 8 independent loads in flight, summed in slice order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (c0 + u < a.nparts) ? __ldcs(src + (size_t)(c0 + u) * nj) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+      }
     }
     g_s[(cl * kp + 4 * q + e) * B2H_KW + k] = s;
   }
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(256) adam_gp_tile_kernel(AdamArgs a) {
     float s = 0.f;
     if (co < cout) {
       const size_t j = base + (size_t)B2H_KW * cout * kp + co;
-      for (int c = 0; c < a.nparts; ++c) s += __ldcs(a.grads + (size_t)c * nj + j);
+      for (int c = 0; c < a.nparts; ++c) s += __ldcs(a.grads + (size_t)c * nj + j);     // same slice order as above
     }
     b_s[threadIdx.x] = s;
   }
@@ -209,7 +215,7 @@ __global__ void __launch_bounds__(256) adam_gp_tile_kernel(AdamArgs a) {
   // (3) slot order again: scatter the new weights into the packed operand layouts
   if (a.packed) {
     for (int idx = threadIdx.x; idx < nslot; idx += blockDim.x) {
-      const int e = idx & 3, cl = (idx >> 2) & (kAdamCoGroup - 1), r = idx >> 4;
+      const int e = idx & 3, cl = (idx >> 2) % kAdamCoGroup, r = idx / (4 * kAdamCoGroup);
       const int q = r % q4, k = r / q4;
       const int co = co0 + cl, ci = 4 * q + e;
       if (co < cout && ci < cin) {
