@@ -276,9 +276,7 @@ static int train_common(const void* x, int x_dtype, const float* target, const f
     return launch_tc_tile_train(a, stream, is_split(precision));
   }
   if (plan.kernel == B2H_KERNEL_TC_WIDE_TRAIN) {
-    // the device-side counters are bumped by a one-thread kernel-free path: the wide kernels do not touch them, the Adam
-    // kernel reads step_dev -- so advance it here with a tiny launch of the reduce-free counter kernel
-    if (step_dev || epoch_dev) { if (int rc = launch_bump_counters(step_dev, epoch_dev, stream)) return rc; }
+    // (the forward+criterion kernel's CTA 0 bumps the device-side step / epoch counters the Adam kernels read)
     return launch_tc_wide_train(a, reinterpret_cast<unsigned char*>(workspace) + plan.scratch_off, stream);
   }
   return launch_fp32(a, true, stream, nparts);

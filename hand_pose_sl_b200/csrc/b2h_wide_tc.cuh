@@ -48,6 +48,7 @@ struct WideArgs {
   long long tile_bytes;         // dump of the shared-memory operand layout [channel/8][264 rows][8 ch] bf16
   long long act_off[4], dz_off[4];
   float* loss_partials;         // [grid]
+  long long* step_dev; long long* epoch_dev;   // MODE 1: device-side step / exchange-epoch counters, bumped by CTA 0 (read by the Adam kernel)
 };
 
 constexpr int kWideThreads = 320;
@@ -150,6 +151,10 @@ __global__ void __launch_bounds__(kWideThreads, 1) conv_tc_wide_kernel(WideArgs 
     mbar_init(&acc_full, 1);
     mbar_init(&act_ready, kWideEpiThreads);
     fence_barrier_init();
+    if (MODE == 1 && blockIdx.x == 0) {
+      if (p.step_dev) *p.step_dev += 1;
+      if (p.epoch_dev) *p.epoch_dev += 1;
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -812,6 +817,7 @@ int launch_tc_wide_train(const Fp32Args& a, unsigned char* scratch, cudaStream_t
   p.apply_mask = 1; p.out_scale = 1.0f;
   p.target = a.target; p.conf = a.conf; p.d_y = a.d_y; p.loss_kind = a.loss_kind; p.train_mode = a.mode;
   p.scratch = scratch; p.loss_partials = a.loss_partials;
+  p.step_dev = a.step_dev; p.epoch_dev = a.epoch_dev;
   size_t smem; int grid;
   if (int rc = wide_common(p, g, a.B, a.T, smem, grid)) return rc;
   // ---- 1. forward + criterion ----
