@@ -28,7 +28,7 @@ for prec in ("bf16",):
         fr.run(0)
 m = b2h.ConvModel(30, "ReLU", False, precision=(sys.argv[2] if len(sys.argv) > 2 else "bf16")).to(dev)
 opt = b2h.FusedAdam(m.parameters(), lr=2e-4)
-r = TrainStepRunner(m, opt, 256, 64)
+r = TrainStepRunner(m, opt, 256, 64, x_dtype=torch.bfloat16 if (len(sys.argv) <= 2 or sys.argv[2] == "bf16") else None)   # as benched: bf16 keypoint input
 r.load(synthetic.model_batch(256, 64, seed=1234), non_blocking=False)
 for _ in range(reps):
     r.step(0)
