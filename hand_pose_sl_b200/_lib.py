@@ -68,6 +68,7 @@ _SIGNATURES = {
                                   c_double, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                   c_void_p, c_int64, c_void_p]),
     "b2h_dp_exchange_floats": (c_int64, [c_int, c_int, c_int, c_int]),
+    "b2h_dp_exchange_fill": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "b2h_dp_status": (c_int, []),
     "b2h_pos_emb_concat": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b2h_format_prediction": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),

@@ -335,6 +335,12 @@ extern "C" int64_t b2h_dp_exchange_floats(int n_in, int C, int pos_emb, int worl
   return 4 * (int64_t)world * gp_total(g) + 64;
 }
 
+extern "C" int64_t b2h_dp_exchange_fill(int T, int n_in, int C, int pos_emb, int precision) {
+  if (!geo_ok(n_in, C, pos_emb, "b2h_dp_exchange_fill")) return B2H_ESHAPE;
+  // fused tile kernel: every 32-bit word starts as the "not arrived" sentinel; three-launch path: zeroed gradients + flags
+  return train_plan(make_geo(n_in, C, pos_emb), 1, T, precision).kernel == B2H_KERNEL_TC_TILE ? 0xFFFFFFFFll : 0ll;
+}
+
 extern "C" int b2h_dp_status(void) { return dp_status_and_clear(); }
 
 extern "C" int b2h_conv_backward(const void* x, int x_dtype, const float* d_y, const float* params, const void* packed,

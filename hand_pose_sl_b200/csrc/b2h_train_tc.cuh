@@ -61,6 +61,7 @@ constexpr int kAccCol = 0;        // forward / dgrad accumulator: columns [0, 64
 // weight-gradient accumulators follow the forward/dgrad accumulators: 2 layer pairs x (5 taps x 32 + 8 bias) columns
 constexpr int kWgPairCols = 5 * 32 + 8;
 constexpr int kGatherDepth = 24; // independent 16-B loads in flight per thread in the cross-CTA gradient gather
+constexpr uint32_t kDpSentinel = 0xFFFFFFFFu;   // "not arrived yet" in the data-parallel exchange buffer (see the train kernel tail)
 constexpr int kDpMaxCta = 160;    // flag slots per rank in the data-parallel exchange buffer (>= CTAs of the train kernel)
 
 struct TileSmem {   // byte offsets into dynamic smem
@@ -850,11 +851,13 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
         if (lane == 0) *f.loss_out = sl;
       }
-      // Data-parallel exchange buffer (per rank, peer-mapped): uint64 words [2 (epoch parity)][world (source rank)][nj],
-      // each word = {fp32 gradient slot, 32-bit epoch tag} written with ONE 8-byte store ("LL" protocol): the tag
-      // travels with the data, so there are no flags, no fences and no second grid barrier.
+      // Data-parallel exchange buffer (per rank, peer-mapped): 32-bit words [2 (epoch parity)][world (source rank)][nj].
+      // A word is either the SENTINEL (a NaN pattern no arithmetic produces) or a peer's fp32 gradient slot: the value is its
+      // own arrival flag, so a slot costs 4 bytes on the wire (round 1's {value, epoch tag} words cost 8: at 8 ranks the
+      // 1.36 MB of ingress per step were ~1.5 us of NVLink time).  The reader puts the sentinel back right after reading;
+      // the parity double-buffers against a peer that is one step ahead (it cannot be two ahead: it needs this rank's words
+      // of the step in between, which are pushed by the NEXT launch, after this launch's resets are complete).
       const long long epoch = epoch_next;
-      const uint32_t tag = (uint32_t)epoch;
       const size_t ll_src = ((size_t)(epoch & 1) * f.world + f.rank) * nj;
       // Latency-bound L2 gather of this CTA's `per` slots over all CTA slices: float4 columns x part groups, 16
       // independent 16-B loads in flight per thread, fixed summation order (deterministic).
@@ -899,23 +902,23 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
             // in rank order (identical arithmetic on every rank).  With a multicast (NVLS) mapping of the exchange
             // buffers ONE multimem.st is replicated by the NVSwitch into every rank's buffer; otherwise W unicast
             // 8-byte stores (coalesced per warp, fire-and-forget over NVLink).
-            const unsigned long long word = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(gr);
+            uint32_t word = __float_as_uint(gr);
+            if (word == kDpSentinel) word = 0x7FC00000u;               // (a NaN gradient stays a NaN, never the sentinel)
             if (f.mc_buf) {
-              asm volatile("multimem.st.relaxed.sys.global.b64 [%0], %1;" ::"l"(f.mc_buf + ll_src + j), "l"(word) : "memory");
+              asm volatile("multimem.st.relaxed.sys.global.b32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(f.mc_buf) + ll_src + j), "r"(word) : "memory");
             } else {
               for (int r = 0; r < f.world; ++r)
-                *(reinterpret_cast<volatile unsigned long long*>(const_cast<float*>(f.peer_bufs[r])) + ll_src + j) = word;
+                *(reinterpret_cast<volatile uint32_t*>(const_cast<float*>(f.peer_bufs[r])) + ll_src + j) = word;
             }
             B2H_STAMP();   // tail: slot pushed
             float gsum = 0.f;
-            const volatile unsigned long long* mine =
-                reinterpret_cast<const volatile unsigned long long*>(f.peer_bufs[f.rank]) + (size_t)(epoch & 1) * f.world * nj + j;
+            volatile uint32_t* mine = reinterpret_cast<volatile uint32_t*>(const_cast<float*>(f.peer_bufs[f.rank])) + (size_t)(epoch & 1) * f.world * nj + j;
             const long long t0 = clock64();
             for (int rb = 0; rb < f.world; rb += 8) {
-              // All (<= 8) ranks' words are requested together and the whole group is re-read until every tag matches:
+              // All (<= 8) ranks' words are requested together and the whole group is re-read until every one has arrived:
               // one L2 round trip per polling round.  (Round 1 re-polled the missing words one after the other -- at 8
               // ranks the first read comes back stale for almost everyone, which cost one round trip PER RANK.)
-              unsigned long long w[8];
+              uint32_t w[8];
               bool all_here;
               do {
 #pragma unroll
@@ -924,7 +927,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
                 all_here = true;
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
-                  if (rb + u < f.world) all_here = all_here && ((uint32_t)(w[u] >> 32) == tag);
+                  if (rb + u < f.world) all_here = all_here && (w[u] != kDpSentinel);
                 if (!all_here && clock64() - t0 > 6000000000LL) {        // ~3 s: a peer never arrived
                   atomicExch(&g_tc_status, 51);
                   atomicExch(&g_dp_abort, 1);
@@ -934,7 +937,10 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
               } while (!all_here);
 #pragma unroll
               for (int u = 0; u < 8; ++u)
-                if (rb + u < f.world) gsum += __uint_as_float((uint32_t)w[u]);       // rank order: identical arithmetic on every rank
+                if (rb + u < f.world) {
+                  gsum += __uint_as_float(w[u]);                       // rank order: identical arithmetic on every rank
+                  if (!aborted) mine[(size_t)(rb + u) * nj] = kDpSentinel;   // re-arm the word for the step after next
+                }
             }
             B2H_STAMP();   // tail: world's slots collected
             gr = gsum;

@@ -62,14 +62,14 @@ def broadcast_parameters(model: ConvModel, src: int = 0, group=None):
         model.mark_packed_stale()
 
 
-def _symmetric_exchange_buffer(n_floats: int, device, group):
+def _symmetric_exchange_buffer(n_floats: int, device, group, fill: int = 0):
     """Peer-mapped exchange buffer on every rank (torch symmetric memory: cuMem allocations mapped into every peer over
     NVLink, plus -- when the fabric supports it -- one multicast (NVLS) address that reaches all of them).  Returns
     (local tensor, handle, device array of peer base pointers indexed by rank, multicast address or 0)."""
     import torch.distributed._symmetric_memory as symm_mem
     world = dist.get_world_size(group)
     buf = symm_mem.empty(n_floats, dtype=torch.float32, device=device)
-    buf.zero_()
+    buf.view(torch.int32).fill_(fill - (1 << 32) if fill >= (1 << 31) else fill)     # b2h_dp_exchange_fill: sentinel or zero
     hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
     ptrs = [int(p) for p in hdl.buffer_ptrs]
     if len(ptrs) != world or hdl.rank != dist.get_rank(group):
@@ -111,7 +111,8 @@ class DataParallelTrainer(_StepBuffers):
             try:
                 n_in_, C_, pe_ = model._geometry()
                 nfl = int(self.lib.b2h_dp_exchange_floats(n_in_, C_, pe_, self.world))
-                self.sym, self.sym_hdl, self.peer_ptrs, mc = _symmetric_exchange_buffer(nfl, dev, group)
+                fill = int(self.lib.b2h_dp_exchange_fill(T, n_in_, C_, pe_, _lib.PRECISIONS[model.precision]))
+                self.sym, self.sym_hdl, self.peer_ptrs, mc = _symmetric_exchange_buffer(nfl, dev, group, fill)
                 self.mc_ptr = mc if multicast else 0
                 self.peers_seen = int(self.peer_ptrs.numel())
                 self.epoch_dev = torch.zeros((1,), dtype=torch.int64, device=dev)

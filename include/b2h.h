@@ -216,10 +216,15 @@ int b2h_adam_step_dp(float* params, const void* peer_bufs_dev, int rank, int wor
                      int pos_emb, void* stream);
 /* floats a rank's exchange buffer must hold for b2h_train_step_dp / b2h_adam_step_dp */
 int64_t b2h_dp_exchange_floats(int n_in, int C, int pos_emb, int world);
+/* 32-bit pattern every word of the exchange buffer must be filled with ONCE, before the first step, on every rank:
+ * 0xFFFFFFFF for shapes the one-launch tile kernel serves (its exchange words are 4 bytes: the gradient value is its own
+ * arrival flag, "not arrived" = this NaN pattern, re-armed by the reader), 0 for the three-launch path (gradients + flags). */
+int64_t b2h_dp_exchange_fill(int T, int n_in, int C, int pos_emb, int precision);
 
 /* The whole data-parallel step as ONE call; in bf16 mode (tensor-core tile kernel) also ONE cooperative kernel
  * launch per rank: forward + loss + backward, grid barrier, cross-CTA reduction, gradient exchange over peer memory
- * (8-byte {value, epoch tag} words pushed into every rank's buffer), sum in rank order, Adam + re-pack.
+ * (4-byte words pushed into every rank's buffer; the value is its own arrival flag, see b2h_dp_exchange_fill), sum in
+ * rank order, Adam + re-pack.
  * multicast_buf (nullable): the multicast (NVLS) address of the ranks' exchange buffers
  * (torch symmetric-memory handle .multicast_ptr): the push is then ONE multimem.st per gradient slot, replicated by
  * the NVSwitch, instead of `world` unicast stores.  lr_dev: see b2h_adam_step.  A wait for a peer that exceeds ~3 s
