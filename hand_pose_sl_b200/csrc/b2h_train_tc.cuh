@@ -334,10 +334,14 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   // tag can be computed before the barrier.  Separate-launch paths: CTA 0 bumps them now for the kernels that follow.
   long long step_next = 0, epoch_next = 0;
   unsigned sync_tok = 0;
+  int abort_flag = 0;
   if (TRAIN) {
     if (p.fuse.enabled) {
       step_next = *reinterpret_cast<const volatile long long*>(p.fuse.step_dev) + 1;
-      if (p.fuse.world > 1) epoch_next = *reinterpret_cast<const volatile long long*>(p.fuse.epoch_dev) + 1;
+      if (p.fuse.world > 1) {
+        epoch_next = *reinterpret_cast<const volatile long long*>(p.fuse.epoch_dev) + 1;
+        abort_flag = *reinterpret_cast<volatile int*>(&g_dp_abort);
+      }
       sync_tok = *reinterpret_cast<const volatile unsigned*>(p.fuse.hdr) + 1u;
     } else if (blockIdx.x == 0 && tid == 0) {
       if (p.step_dev) *p.step_dev += 1;
@@ -835,7 +839,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         my_m = __ldcg(f.m + my_i); my_v = __ldcg(f.v + my_i); my_p = __ldcg(f.params + my_i);
       }
       B2H_MARK(1);
-      bool aborted = dp && (*reinterpret_cast<volatile int*>(&g_dp_abort) != 0);   // set by an earlier step's peer timeout
+      bool aborted = abort_flag != 0;                    // set by an earlier step's peer timeout (fetched at kernel start)
       grid_barrier_flags(f.hdr, sync_tok, tid);          // every CTA's partial slice is visible
       B2H_STAMP();   // tail: grid barrier passed
       B2H_MARK(2);
