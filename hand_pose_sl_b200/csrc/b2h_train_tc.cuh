@@ -50,6 +50,12 @@ struct TcTileArgs {
   // w, frame t reads row win_start[w] + t of it (cut at win_end[w] / n_frames, then the dataset's pad rule) -- overlapping
   // windows are views of the stream, nothing is re-materialised.
   const long long* win_start; const long long* win_end; long long n_frames; int pad_mode;
+  // Sub-window training (n_sub > 1; fp32 mode, 128 < T_orig <= 256): the doubled operand buffers only fit 128-frame
+  // segments, so every window is processed as n_sub overlapping 128-frame sub-windows that read REAL neighbouring frames
+  // (>= 16 on each interior side) instead of zero padding; the criterion (and d_y) is applied to the sub-window's core
+  // rows only.  The backward is linear in d(loss)/d(pred) and the activations are exact up to 8 frames from a cut, so the
+  // sum of the sub-windows' weight gradients is the window's gradient.  B / T are then the sub-window count / length.
+  int T_orig, n_sub, loss_B;
   int B, T, loss_kind, apply_mask, mode;   // mode 0 = forward only, 1 = train (loss inside), 2 = backward of given d_y
   float out_scale;
   int n_tiles, nhalf, MB, HR, gh, NT;      // tile geometry (NT = 128-row MMA tiles per segment: 2 for 128 < T <= 256)
@@ -274,8 +280,28 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
   // source row of (window gw, frame tt) in p.x; -1 = a zero row.  Dense batches: gw*T + tt.  Window views of a frame
   // stream: crop [start, start+T) cut at the clip end, then the pad rule (repeat the crop's first frame:
   // text_pose_dataset.py:511-518; zeros: :614-622) -- the same integer work as K0's windowing, bit-exact.
+  // sub-window gw -> (window b, first frame, core rows [clo, chi)); identity when n_sub <= 1
+  struct SubW { int b, start, clo, chi; };
+  auto subw = [&](int gw) {
+    SubW sw;
+    if (p.n_sub <= 1) { sw.b = gw; sw.start = 0; sw.clo = 0; sw.chi = T; return sw; }
+    sw.b = gw / p.n_sub;
+    const int i = gw - sw.b * p.n_sub;
+    const int cb0 = (int)((long long)i * p.T_orig / p.n_sub), cb1 = (int)((long long)(i + 1) * p.T_orig / p.n_sub);
+    int st = cb0 - 16;
+    st = st < 0 ? 0 : st;
+    st = st > p.T_orig - T ? p.T_orig - T : st;
+    sw.start = st; sw.clo = cb0 - st; sw.chi = cb1 - st;
+    return sw;
+  };
+  // row of (window gw, frame tt) in the dense (B, T, .) arrays (inputs, targets, scores, d_y, prediction)
+  auto dense_row = [&](int gw, int tt) -> long long {
+    if (p.n_sub <= 1) return (long long)gw * T + tt;
+    const SubW sw = subw(gw);
+    return (long long)sw.b * p.T_orig + sw.start + tt;
+  };
   auto xrow_of = [&](int gw, int tt) -> long long {
-    if (!p.win_start) return (long long)gw * T + tt;
+    if (!p.win_start) return dense_row(gw, tt);
     const long long start = p.win_start[gw];
     long long cend = p.win_end ? p.win_end[gw] : p.n_frames;
     cend = cend > p.n_frames ? p.n_frames : cend;
@@ -414,11 +440,12 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
       const RowCtx rc = rowctx(j, wbase);
-      lens[j] = T;
-      if (rc.valid && p.lengths) { const int v = p.lengths[rc.gw]; lens[j] = v < 0 ? 0 : (v > T ? T : v); }
+      const int Tw = p.n_sub > 1 ? p.T_orig : T;              // length of the window the sequence length refers to
+      lens[j] = Tw;
+      if (rc.valid && p.lengths) { const int v = p.lengths[p.n_sub > 1 ? rc.gw / p.n_sub : rc.gw]; lens[j] = v < 0 ? 0 : (v > Tw ? Tw : v); }
     }
 
-    const bool tgt_smem = TRAIN && p.mode == 1 && bulk_io;
+    const bool tgt_smem = TRAIN && p.mode == 1 && bulk_io && p.n_sub <= 1;
     if (tid == 0) {
       if (!TRAIN) bulk_wait_read0();              // previous tile's y stores have read the staging tile
       if (tgt_smem) {                             // target rows of this tile's windows -> staging tile (TMA bulk loads)
@@ -464,7 +491,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           for (int e = 0; e < 8; ++e) {
             const int cc = c8 * 8 + e;            // channel in the conv1 input (pos-emb row first)
             float val = 0.0f;
-            if (pe && cc == 0) val = __fdiv_rn((float)rc.t, (float)g.pe_len);             // HandPoseModels.py:70-82
+            if (pe && cc == 0) val = __fdiv_rn((float)(subw(rc.gw).start + rc.t), (float)g.pe_len);   // HandPoseModels.py:70-82
             else if (cc - pe < n_in && cc - pe >= 0 && xr >= 0) {
               const size_t gi = (size_t)xr * n_in + (cc - pe);
               val = (p.x_dtype == B2H_DT_F32) ? __ldg(reinterpret_cast<const float*>(p.x) + gi)
@@ -537,21 +564,28 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         }
       } else {
         // layer 4 epilogue: prediction (+ mask_output), and in train mode the criterion and d(loss)/d(pred)
-        const int len = lens[j];
+        int len = lens[j];
         float n_el = 0.f, scale = 0.f;
         const float* tg = nullptr; const float* cf = nullptr; const float* dy = nullptr;
+        const size_t drow = valid ? (size_t)dense_row(gw, t) : 0;       // row of this frame in the dense (B, T, .) arrays
+        bool in_core = true;
         if (TRAIN && valid) {
-          n_el = (float)len * (float)B2H_COUT;
-          scale = (p.loss_kind == B2H_LOSS_L1) ? (1.0f / (float)p.B) / n_el : 1.0f / n_el;
+          n_el = (float)len * (float)B2H_COUT;                      // (sub-window mode: len = the WINDOW's sequence length)
+          scale = (p.loss_kind == B2H_LOSS_L1) ? (1.0f / (float)p.loss_B) / n_el : 1.0f / n_el;
+          if (p.n_sub > 1) {                                        // criterion on the core rows only; len -> sub-window frames
+            const SubW sw = subw(gw);
+            in_core = t >= sw.clo && t < sw.chi;
+            len -= sw.start;
+          }
           if (p.mode == 1) {
-            tg = p.target + ((size_t)gw * T + t) * B2H_COUT;        // global copy (used when the tile is not staged)
-            cf = p.conf ? p.conf + ((size_t)gw * T + t) * (B2H_COUT / 2) : nullptr;
+            tg = p.target + drow * B2H_COUT;                        // global copy (used when the tile is not staged)
+            cf = p.conf ? p.conf + drow * (B2H_COUT / 2) : nullptr;
           } else {
-            dy = p.d_y + ((size_t)gw * T + t) * B2H_COUT;
+            dy = p.d_y + drow * B2H_COUT;
           }
         }
         const bool y_smem = !TRAIN && bulk_io;
-        float* yrow = (valid && p.y) ? p.y + ((size_t)gw * T + t) * B2H_COUT : nullptr;          // global row
+        float* yrow = (valid && p.y && in_core) ? p.y + drow * B2H_COUT : nullptr;                // global row
         float* ys_row = YS + (size_t)srow * B2H_COUT;                                            // shared staging row
         if (tgt_smem && j == 0) { mbar_wait(&tbar, tphase, 18); tphase ^= 1; }
         B2H_STAMP();   // layer-4 epilogue: target tile landed
@@ -562,7 +596,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
         // layer's epilogue (per-element predicates for the confidence weights, the given-d_y mode and the y store).
         const bool l4_fast = TRAIN && p.mode == 1 && p.loss_kind == B2H_LOSS_L1 && tgt_smem && p.y == nullptr;
         if (TRAIN && l4_fast) {
-          const bool live = valid && (t < len);          // rows t >= len are zeroed by mask_output and carry no loss
+          const bool live = valid && (t < len) && in_core;   // rows t >= len are zeroed by mask_output and carry no loss
           auto chunk = [&](auto c0_tag) {
             constexpr int C0 = decltype(c0_tag)::value;
             uint32_t v[16];
@@ -619,7 +653,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           } else {
             // training epilogue, branch-free per element: masked prediction, criterion term, d(loss)/d(pred).
             // L1 is the confidence-weighted form with s = 1 (a*1 - t*1 == a - t exactly).   utils.py:422-426 / :447-450
-            const bool live = valid && (t < len);          // rows t >= len are zeroed by mask_output and carry no loss
+            const bool live = valid && (t < len) && in_core;   // rows t >= len are zeroed by mask_output and carry no loss
             float tvals[16], svals[16];
 #pragma unroll
             for (int q = 0; q < 16; q += 2) {
@@ -655,7 +689,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
           B2H_STAMP();   // layer-4 epilogue: one 16-column chunk done
         }
         // per-sample mean = sum_{t<len} |d| / (len*42)  (utils.py:426 / :450): accumulate sum/n_el
-        if (TRAIN && p.mode == 1) contrib += (valid && t < len) ? sum / n_el : 0.f;
+        if (TRAIN && p.mode == 1) contrib += (valid && t < len && in_core) ? sum / n_el : 0.f;
       }
       }   // MMA tiles j
       if (TRAIN && p.mode == 1 && l == 3) {
@@ -805,7 +839,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       if (!pair1_done) readout_pair(1);
     }
     if (tid == 0 && p.loss_partials)
-      p.loss_partials[blockIdx.x] = (p.loss_kind == B2H_LOSS_L1) ? loss_acc / (float)p.B : loss_acc;
+      p.loss_partials[blockIdx.x] = (p.loss_kind == B2H_LOSS_L1) ? loss_acc / (float)p.loss_B : loss_acc;
     B2H_STAMP();   // partial slice written
 
     if (p.fuse.enabled) {
@@ -984,10 +1018,18 @@ inline size_t tc_tile_smem(const Geo& g, int T, bool train, bool split) {
   return (size_t)tile_smem_layout(g, nhalf * (MB + 8), train, split).total;
 }
 
+// fp32-mode training of windows longer than 128 frames: n_sub overlapping 128-frame sub-windows (see TcTileArgs), every cut
+// with >= 16 real frames of context on both sides: two sub-windows cover T <= 224, three T <= 320
+inline int tc_tile_nsub(int T, bool train, bool split) {
+  if (!(train && split) || T <= 128) return 1;
+  return T <= 224 ? 2 : 3;
+}
+
 inline bool tc_tile_supported(const Geo& g, int T, bool train, bool split) {
   if (T < 1 || T > 256) return false;
   if ((g.kp[0] > 32 || g.kp[1] > 32) && (train || split || g.kp[0] > 64 || g.kp[1] > 64)) return false;
-  return tc_tile_smem(g, T, train, split) <= (size_t)225 * 1024;
+  const int Tk = tc_tile_nsub(T, train, split) > 1 ? 128 : T;
+  return tc_tile_smem(g, Tk, train, split) <= (size_t)225 * 1024;
 }
 
 inline void tc_tile_plan(const Geo& g, int B, int T, bool train, bool split, TcTileArgs& p, size_t& smem, int& grid) {
@@ -1008,7 +1050,8 @@ inline void tc_tile_plan(const Geo& g, int B, int T, bool train, bool split, TcT
 int tc_train_grid(const Geo& g, int B, int T, bool split) {
   TcTileArgs p{};
   size_t smem; int grid;
-  tc_tile_plan(g, B, T, true, split, p, smem, grid);
+  const int ns = tc_tile_nsub(T, true, split);
+  tc_tile_plan(g, ns > 1 ? B * ns : B, ns > 1 ? 128 : T, true, split, p, smem, grid);
   return grid;
 }
 
@@ -1063,6 +1106,8 @@ int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream, bool split) {
   p.out_scale = 1.0f; p.geo = a.geo;
   p.fuse = a.fuse;
   p.dbg = g_dbg_timing;
+  p.loss_B = a.B; p.T_orig = a.T; p.n_sub = tc_tile_nsub(a.T, true, split);
+  if (p.n_sub > 1) { p.B = a.B * p.n_sub; p.T = 128; }
   return launch_tc_tile(p, true, split, stream);
 }
 
