@@ -24,7 +24,7 @@ def _grads_close(v, ref, prec, tol):
     operand carries bf16 high + low halves (16-17 significant bits, ~6e-6 relative on an activation), so a ReLU or an
     L1-sign decision that the fp32 reference takes within that distance of zero can fall the other way; ONE flipped ReLU
     moves ONE output channel's gradient by one frame's contribution (~1e-3 of its scale at 3 windows).  The check is
-    therefore: tol on all but <= 1 % of the elements, 1e-2 everywhere (seen on convmodel_c30_t200, window 3, conv1 channel 3;
+    therefore: tol everywhere except in at most two output channels, 1e-2 there (seen on convmodel_c30_t200, window 3, conv1 channel 3;
     fp32-ffma, which is exact to ~1e-7, agrees with the reference there to 5e-7)."""
     err = oracle.rel_err(v, ref)
     if err <= tol:
@@ -32,7 +32,8 @@ def _grads_close(v, ref, prec, tol):
     if prec != "fp32":
         return False
     bad = np.abs(v - ref) > tol * np.abs(ref).max()
-    return bad.mean() <= 0.01 and err <= 1e-2
+    channels_hit = int(bad.reshape(bad.shape[0], -1).any(axis=1).sum())          # axis 0 = output channel
+    return channels_hit <= 2 and err <= 1e-2
 
 
 def _model(sd, C, pe, prec):
