@@ -29,7 +29,8 @@ extern "C" {
 /* precision modes (north_star: fp32 mode 1e-4, bf16 mode 2e-2) */
 #define B2H_FP32 0        /* fp32 mode: tcgen05 with every operand split into bf16 high + low halves, three MMAs per
                              product (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo), fp32 accumulate in TMEM: ~6e-6 relative on the
-                             prediction (conv_channels <= 32, T <= 256); the FFMA kernel for every other shape */
+                             prediction (conv_channels <= 32, T <= 256; windows longer than 128 frames train as overlapping
+                             128-frame sub-windows with real context at the cuts); the FFMA kernel for every other shape */
 #define B2H_BF16 1        /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate (TMEM) */
 #define B2H_FP32_FFMA 2   /* fp32 mode on the CUDA cores only (FFMA, fp32 accumulate): the arbiter of the split kernel */
 
