@@ -29,6 +29,7 @@ _SIGNATURES = {
     "b2h_param_offset": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
     "b2h_packed_bytes": (c_int64, [c_int, c_int, c_int]),
     "b2h_gp_layout_check": (c_int64, [c_int, c_int, c_int]),
+    "b2h_train_subwindows": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "b2h_workspace_bytes": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "b2h_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "b2h_forward_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),

@@ -152,6 +152,25 @@ extern "C" int b2h_kernel_choice(int T, int n_in, int C, int pos_emb, int precis
   if (!prec_ok(precision)) return B2H_KERNEL_NONE;
   return train_plan(g, 1, T, precision).kernel;
 }
+/* How the tile kernel's training path cuts a window of T frames (host-only query): returns n_sub (1 = whole windows) and,
+ * for sub-window i, writes {first frame, first core row, end of the core rows (sub-window coordinates), sub-window length}. */
+extern "C" int b2h_train_subwindows(int T, int n_in, int C, int pos_emb, int precision, int i, int* out4) {
+  if (!geo_ok(n_in, C, pos_emb, "b2h_train_subwindows")) return B2H_ESHAPE;
+  if (T < 1) { set_error("b2h_train_subwindows: bad T"); return B2H_ESHAPE; }
+  Geo g = make_geo(n_in, C, pos_emb);
+  const int n = use_tc_train(g, T, precision) ? tc_train_nsub(T, is_split(precision)) : 1;
+  if (out4) {
+    if (i < 0 || i >= n) { set_error("b2h_train_subwindows: sub-window %d of %d", i, n); return B2H_EINVAL; }
+    if (n == 1) { out4[0] = 0; out4[1] = 0; out4[2] = T; out4[3] = T; }
+    else {
+      const int Ts = tc_train_sub_len(is_split(precision));
+      const SubWindow s = sub_window(T, Ts, n, i);
+      out4[0] = s.start; out4[1] = s.clo; out4[2] = s.chi; out4[3] = Ts;
+    }
+  }
+  return n;
+}
+
 extern "C" int64_t b2h_workspace_bytes(int B, int T, int n_in, int C, int pos_emb, int precision) {
   if (!geo_ok(n_in, C, pos_emb, "b2h_workspace_bytes")) return B2H_ESHAPE;
   if (B < 1 || T < 1) return B2H_WS_HEADER + 256;

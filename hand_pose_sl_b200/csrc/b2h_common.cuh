@@ -192,6 +192,27 @@ __host__ __device__ inline double ipow(double b, long long t) {
   return r;
 }
 
+// Sub-window decomposition of a training window (see TcTileArgs in b2h_train_tc.cuh): window frames [0, T) are cut into
+// n_sub cores [cb_i, cb_{i+1}): the first core takes Ts - 16 frames, every further one Ts - 32 (the last: what is left);
+// sub-window i covers Ts frames from `start` = cb_i - 16 clamped to [0, T - Ts], so that every interior cut has >= 16 real
+// frames of context on both sides.  Core rows in sub-window coordinates: [clo, chi).
+struct SubWindow { int start, clo, chi; };
+__host__ __device__ inline int sub_window_cut(int T, int Ts, int n_sub, int i) {
+  if (i <= 0) return 0;
+  if (i >= n_sub) return T;
+  const int c = (Ts - 16) + (i - 1) * (Ts - 32);
+  return c < T ? c : T;
+}
+__host__ __device__ inline SubWindow sub_window(int T, int Ts, int n_sub, int i) {
+  SubWindow s;
+  const int cb0 = sub_window_cut(T, Ts, n_sub, i), cb1 = sub_window_cut(T, Ts, n_sub, i + 1);
+  int st = cb0 - 16;
+  st = st < 0 ? 0 : st;
+  st = st > T - Ts ? T - Ts : st;
+  s.start = st; s.clo = cb0 - st; s.chi = cb1 - st;
+  return s;
+}
+
 // Workspace header of the fused train kernel (first B2H_WS_HEADER bytes of the caller's workspace, zeroed once when the
 // workspace is allocated and owned by the kernels afterwards; FIXED offset, so runners of different (B, T) that share
 // one workspace can never find gradient partials where they expect barrier words):
@@ -266,6 +287,8 @@ int tc_status_and_clear();
 
 struct TcTileArgs;
 int tc_train_grid(const Geo& g, int B, int T, bool split);
+int tc_train_nsub(int T, bool split);        // sub-windows per window of the tile kernel's training path (1 = whole windows)
+int tc_train_sub_len(bool split);            // their length: 128 frames in fp32 (split) mode, 256 in bf16 mode
 bool tc_tile_ok(const Geo& g, int T, bool train, bool split);   // split = fp32 mode on the tensor pipe (bf16 high/low operand pairs)
 struct WindowView { const long long* win_start; const long long* win_end; long long n_frames; int pad_mode; };
 int launch_tc_tile_fwd(const void* x, int x_dtype, const float* params, const char* packed, const int32_t* lengths, float* y,

@@ -50,8 +50,8 @@ struct TcTileArgs {
   // w, frame t reads row win_start[w] + t of it (cut at win_end[w] / n_frames, then the dataset's pad rule) -- overlapping
   // windows are views of the stream, nothing is re-materialised.
   const long long* win_start; const long long* win_end; long long n_frames; int pad_mode;
-  // Sub-window training (n_sub > 1; fp32 mode, 128 < T_orig <= 256): the doubled operand buffers only fit 128-frame
-  // segments, so every window is processed as n_sub overlapping 128-frame sub-windows that read REAL neighbouring frames
+  // Sub-window training (n_sub > 1: T_orig > 128 in fp32 mode, > 256 in bf16 mode): a tile segment holds 128 (doubled
+  // operand buffers) / 256 frames, so every window is processed as n_sub overlapping sub-windows that read REAL neighbouring frames
   // (>= 16 on each interior side) instead of zero padding; the criterion (and d_y) is applied to the sub-window's core
   // rows only.  The backward is linear in d(loss)/d(pred) and the activations are exact up to 8 frames from a cut, so the
   // sum of the sub-windows' weight gradients is the window's gradient.  B / T are then the sub-window count / length.
@@ -286,12 +286,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
     SubW sw;
     if (p.n_sub <= 1) { sw.b = gw; sw.start = 0; sw.clo = 0; sw.chi = T; return sw; }
     sw.b = gw / p.n_sub;
-    const int i = gw - sw.b * p.n_sub;
-    const int cb0 = (int)((long long)i * p.T_orig / p.n_sub), cb1 = (int)((long long)(i + 1) * p.T_orig / p.n_sub);
-    int st = cb0 - 16;
-    st = st < 0 ? 0 : st;
-    st = st > p.T_orig - T ? p.T_orig - T : st;
-    sw.start = st; sw.clo = cb0 - st; sw.chi = cb1 - st;
+    const SubWindow q = sub_window(p.T_orig, T, p.n_sub, gw - sw.b * p.n_sub);
+    sw.start = q.start; sw.clo = q.clo; sw.chi = q.chi;
     return sw;
   };
   // row of (window gw, frame tt) in the dense (B, T, .) arrays (inputs, targets, scores, d_y, prediction)
@@ -1018,17 +1014,23 @@ inline size_t tc_tile_smem(const Geo& g, int T, bool train, bool split) {
   return (size_t)tile_smem_layout(g, nhalf * (MB + 8), train, split).total;
 }
 
-// fp32-mode training of windows longer than 128 frames: n_sub overlapping 128-frame sub-windows (see TcTileArgs), every cut
-// with >= 16 real frames of context on both sides: two sub-windows cover T <= 224, three T <= 320
+// Training of windows longer than one tile segment (128 frames in fp32 mode, 256 in bf16 mode): n_sub overlapping
+// sub-windows of Ts frames (see TcTileArgs), every cut with >= 16 real frames of context on both sides: the two edge
+// sub-windows carry up to Ts - 16 core frames, the interior ones Ts - 32.
+constexpr int kTileMaxTrainT = 4096;
+inline int tc_tile_sub_len(bool split) { return split ? 128 : 256; }
 inline int tc_tile_nsub(int T, bool train, bool split) {
-  if (!(train && split) || T <= 128) return 1;
-  return T <= 224 ? 2 : 3;
+  const int Ts = tc_tile_sub_len(split);
+  if (!train || T <= Ts) return 1;
+  int n = 2;
+  while (2 * (Ts - 16) + (n - 2) * (Ts - 32) < T) ++n;
+  return n;
 }
 
 inline bool tc_tile_supported(const Geo& g, int T, bool train, bool split) {
-  if (T < 1 || T > 256) return false;
+  if (T < 1 || T > (train ? kTileMaxTrainT : 256)) return false;
   if ((g.kp[0] > 32 || g.kp[1] > 32) && (train || split || g.kp[0] > 64 || g.kp[1] > 64)) return false;
-  const int Tk = tc_tile_nsub(T, train, split) > 1 ? 128 : T;
+  const int Tk = tc_tile_nsub(T, train, split) > 1 ? tc_tile_sub_len(split) : T;
   return tc_tile_smem(g, Tk, train, split) <= (size_t)225 * 1024;
 }
 
@@ -1047,11 +1049,14 @@ inline void tc_tile_plan(const Geo& g, int B, int T, bool train, bool split, TcT
   if (grid > p.n_tiles) grid = p.n_tiles;
 }
 
+int tc_train_nsub(int T, bool split) { return tc_tile_nsub(T, true, split); }
+int tc_train_sub_len(bool split) { return tc_tile_sub_len(split); }
+
 int tc_train_grid(const Geo& g, int B, int T, bool split) {
   TcTileArgs p{};
   size_t smem; int grid;
   const int ns = tc_tile_nsub(T, true, split);
-  tc_tile_plan(g, ns > 1 ? B * ns : B, ns > 1 ? 128 : T, true, split, p, smem, grid);
+  tc_tile_plan(g, ns > 1 ? B * ns : B, ns > 1 ? tc_tile_sub_len(split) : T, true, split, p, smem, grid);
   return grid;
 }
 
@@ -1107,7 +1112,7 @@ int launch_tc_tile_train(const Fp32Args& a, cudaStream_t stream, bool split) {
   p.fuse = a.fuse;
   p.dbg = g_dbg_timing;
   p.loss_B = a.B; p.T_orig = a.T; p.n_sub = tc_tile_nsub(a.T, true, split);
-  if (p.n_sub > 1) { p.B = a.B * p.n_sub; p.T = 128; }
+  if (p.n_sub > 1) { p.B = a.B * p.n_sub; p.T = tc_tile_sub_len(split); }
   return launch_tc_tile(p, true, split, stream);
 }
 

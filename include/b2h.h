@@ -66,6 +66,14 @@ int64_t b2h_packed_bytes(int n_in, int C, int pos_emb);
 /* Host-only self-check of the internal gradient-partial slot layout of the tensor-core train kernel (flat parameter
  * index <-> slot bijection, padding slots, float4 alignment); returns the number of violations, 0 = consistent. */
 int64_t b2h_gp_layout_check(int n_in, int C, int pos_emb);
+/* Host-only query of the training path's window decomposition: returns the number of sub-windows a window of T frames is
+ * processed as (1 = whole windows; windows longer than a tile segment -- 128 frames in fp32 mode, 256 in bf16 mode -- are cut
+ * into overlapping sub-windows of that length that read real context frames at the cuts and apply the criterion to their
+ * core rows; T <= 4096) and, when out4 is non-NULL, sub-window i as
+ * {first frame, first core row, end of core rows, sub-window length}.  tests/test_tiling_model.py proves the identity
+ * "sum of the sub-windows' gradients == the window's gradient" for this decomposition on the CPU. */
+int b2h_train_subwindows(int T, int n_in, int C, int pos_emb, int precision, int i, int* out4);
+
 /* bytes of scratch the train entry points need (1-KB header of the fused kernel's grid barrier + per-CTA gradient
  * partials for a deterministic two-stage reduction + loss partials); 16-byte aligned, zeroed once at allocation */
 int64_t b2h_workspace_bytes(int B, int T, int n_in, int C, int pos_emb, int precision);

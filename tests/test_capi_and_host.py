@@ -87,7 +87,7 @@ def test_kernel_choice_pins_the_tensor_core_paths():
     assert fwd(64, 64, _lib.BF16) == TILE and trn(64, 64, _lib.BF16) == WIDE_TRAIN          # C > 32 trains on the wide tcgen05 kernels
     assert fwd(200, 64, _lib.BF16) == ROWSPACE                                              # tile does not fit smem
     assert fwd(257, 30, _lib.BF16) == ROWSPACE and fwd(1000, 30, _lib.BF16) == ROWSPACE
-    assert trn(257, 30, _lib.BF16) == FFMA
+    assert trn(257, 30, _lib.BF16) == TILE and trn(1000, 30, _lib.BF16) == TILE and trn(300, 30, _lib.FP32) == TILE   # sub-windows
     for C in (80, 96, 128, 256):
         for T in (64, 126, 200, 256):
             assert fwd(T, C, _lib.BF16) == WIDE, (T, C)

@@ -141,3 +141,63 @@ def test_tiling_reproduces_the_reference_train_step(B, T, C):
     for k, v in grads.items():
         # float64 model vs the fp32 reference: a residual within fp32 noise of zero may take the other sign (L1)
         assert oracle.rel_err(v, ref_g[k].numpy()) <= 1e-4, k        # observed <= 1e-6 on these seeds
+
+
+@pytest.mark.parametrize("T,prec", [(129, "fp32"), (160, "fp32"), (200, "fp32"), (224, "fp32"), (225, "fp32"), (256, "fp32"), (300, "fp32"),
+                                    (257, "bf16"), (480, "bf16"), (481, "bf16"), (1000, "bf16")])
+def test_subwindow_decomposition_reproduces_the_window_gradient(T, prec):
+    """fp32 mode trains 129..256-frame windows as overlapping 128-frame sub-windows (b2h_train_subwindows): each reads REAL
+    context frames at its cuts and applies the criterion to its core rows only.  CPU proof, with the library's own cut
+    points and the oracle's formulas in float64: the losses and ALL parameter gradients of the sub-windows sum to the
+    window's (the backward is linear in d(loss)/d(pred); activations are exact up to 8 frames from a cut and dZ reaches at
+    most 6 frames beyond the core, so >= 16 frames of context suffice)."""
+    import ctypes
+    import torch
+    import torch.nn.functional as F
+    from hand_pose_sl_b200 import _lib
+    lib = _lib.load()
+    P = _lib.PRECISIONS[prec]
+    Ts = 128 if prec == "fp32" else 256
+    n = lib.b2h_train_subwindows(T, 24, 30, 0, P, 0, None)
+    assert n >= 2 and 2 * (Ts - 16) + (n - 2) * (Ts - 32) >= T and (n == 2 or 2 * (Ts - 16) + (n - 3) * (Ts - 32) < T)
+    assert lib.b2h_train_subwindows(Ts, 24, 30, 0, P, 0, None) == 1
+    subs = []
+    for i in range(n):
+        out = (ctypes.c_int * 4)()
+        assert lib.b2h_train_subwindows(T, 24, 30, 0, P, i, out) == n
+        subs.append(tuple(out))
+    # the cores tile [0, T) and every interior cut has >= 16 frames of context inside its sub-window
+    cores = [(s + lo, s + hi) for s, lo, hi, L in subs]
+    assert cores[0][0] == 0 and cores[-1][1] == T and all(cores[i][1] == cores[i + 1][0] for i in range(n - 1))
+    for i, (s, lo, hi, L) in enumerate(subs):
+        assert L == Ts and 0 <= s <= T - L and (i == 0 or lo >= 16) and (i == n - 1 or hi + 16 <= L)
+    torch.manual_seed(T)
+    sd = {k: v.double() for k, v in oracle.init_params(30, False, seed=T).items()}
+    x = torch.randn(T, 24, dtype=torch.float64) * 0.2
+    tgt = torch.randn(T, 42, dtype=torch.float64) * 0.1
+    length = T - 37
+
+    def grads(xs, ts, live, n_el):            # xs (L,24): forward with zero padding at the ends, L1 over the `live` rows
+        ps = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        h = xs.t()[None]
+        for l in range(1, 5):
+            h = F.conv1d(h, ps[f"conv{l}.weight"], ps[f"conv{l}.bias"], padding=2)
+            if l < 4:
+                h = F.relu(h)
+        pred = h[0].t()
+        loss = ((pred - ts).abs() * live[:, None]).sum() / n_el
+        loss.backward()
+        return loss.detach(), {k: v.grad for k, v in ps.items()}
+
+    live_full = (torch.arange(T) < length).double()
+    ref_loss, ref_g = grads(x, tgt, live_full, length * 42)
+    tot_loss, tot_g = 0.0, None
+    for s, lo, hi, L in subs:
+        t = torch.arange(L)
+        live = ((t >= lo) & (t < hi) & (s + t < length)).double()
+        l_i, g_i = grads(x[s:s + L], tgt[s:s + L], live, length * 42)
+        tot_loss = tot_loss + l_i
+        tot_g = g_i if tot_g is None else {k: tot_g[k] + g_i[k] for k in g_i}
+    assert abs(float(tot_loss) - float(ref_loss)) <= 1e-12 * abs(float(ref_loss))
+    for k in ref_g:
+        assert float((tot_g[k] - ref_g[k]).abs().max()) <= 1e-12 * float(ref_g[k].abs().max()), k
