@@ -24,16 +24,16 @@ def _grads_close(v, ref, prec, tol):
     operand carries bf16 high + low halves (16-17 significant bits, ~6e-6 relative on an activation), so a ReLU or an
     L1-sign decision that the fp32 reference takes within that distance of zero can fall the other way; ONE flipped ReLU
     moves ONE output channel's gradient by one frame's contribution (~1e-3 of its scale at 3 windows).  The check is
-    therefore: tol on >= 90 % of the elements (a flip touches one output channel = 3 % of a layer's weights), 1e-2 everywhere
-    (seen on convmodel_c30_t200, window 3, conv1 channel 3, and with 1443 frames at T = 481; fp32-ffma, which is exact to
-    ~1e-7, agrees with the reference there to 5e-7)."""
+    therefore: max-norm error <= tol, or -- a handful of flips -- relative L1 error <= 5e-4 with every element inside 1e-2 (a
+    missing operand term or an indexing bug shows as >= 1e-2 across the tensor).  Seen on convmodel_c30_t200 (window 3, conv1
+    channel 3) and with 1443 frames at T = 481; fp32-ffma, exact to ~1e-7, agrees with the reference there to 5e-7."""
     err = oracle.rel_err(v, ref)
     if err <= tol:
         return True
     if prec != "fp32":
         return False
-    bad = np.abs(v - ref) > tol * np.abs(ref).max()
-    return bad.mean() <= 0.10 and err <= 1e-2            # >= 90 % of the elements inside tol, every element inside 1e-2
+    rel_l1 = float(np.abs(v - ref).sum() / np.abs(ref).sum())
+    return rel_l1 <= 5e-4 and err <= 1e-2                # a few channels off by ~1e-3 of their scale: tiny in L1, bounded in max
 
 
 def _model(sd, C, pe, prec):
