@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--skip-extras", action="store_true", help="only the headline train-step number")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="multi-GPU gradient exchange")
     ap.add_argument("--no-multicast", action="store_true", help="p2p exchange: unicast stores even when an NVLS mapping exists")
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave the rank's threads / pinned buffers where the OS puts them")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -212,6 +213,11 @@ def main():
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
+    # before the first pinned allocation: the rank's threads and staging buffers go to its GPU's NUMA node
+    from hand_pose_sl_b200.hostbind import bind_host_to_gpu
+    host_numa = {"bound": False, "why": "--no-numa-bind"} if args.no_numa_bind else bind_host_to_gpu(local_rank)
+    if world > 1:
+        sys.stderr.write(f"[bench] rank {rank}: host placement {host_numa}\n")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -356,7 +362,7 @@ def main():
             "repeats": repeats, "timed_steps": timed_steps, "timed_region_ms": ms,
             "config": {"workload": f"train step (fwd+mask+L1+bwd+Adam), batch {B_TRAIN}x{T} frames per GPU, C={C} (BASELINE config 3/4)",
                        "global_batch": B_TRAIN * world, "frames_per_window": T, "conv_channels": C,
-                       "parallelism": f"dp{world}", "cuda_graph": graphed,
+                       "parallelism": f"dp{world}", "cuda_graph": graphed, "host_numa": host_numa,
                        "grad_exchange": (getattr(runner, "exchange", None) if world > 1 else None),
                        "timing": f"{repeats} x {args.steps} steps timed back to back after {max(args.warmup, chunk)} warm-up steps "
                                  f"of the same CUDA graph and one untimed {args.steps}-step pass that aligns the ranks",

@@ -74,6 +74,11 @@ __device__ __forceinline__ bool mbar_wait_warp(uint64_t* bar, uint32_t parity, i
 
 // ---- proxies / fences -------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Programmatic dependent launch (sm_90+).  `launch_dependents`: the next kernel on the stream, if it was launched with the
+// programmatic-serialization attribute, may start its CTAs once every CTA of this grid has passed this point (or exited).
+// `wait`: blocks until the preceding grid has completed and its memory is visible; a no-op for a normal launch.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

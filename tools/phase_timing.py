@@ -22,9 +22,9 @@ if world > 1:
 lib = _lib.load()
 buf = torch.zeros(1024, dtype=torch.int64, device=dev)
 
-FWD = (["start", "setup", "staging", "weights"] + [f"F{l}:{p}" for l in range(3) for p in ("issued", "ready", "epilogue")]
+FWD = (["start", "pre-wait", "setup", "staging", "weights"] + [f"F{l}:{p}" for l in range(3) for p in ("issued", "ready", "epilogue")]
        + ["F3:issued", "F3:ready", "F3:target", "F3:chunk0", "F3:chunk1", "F3:epilogue"])
-TRAIN = (["start", "setup", "staging", "weights"] + [f"F{l}:{p}" for l in range(3) for p in ("issued", "ready", "epilogue")]
+TRAIN = (["start", "pre-wait", "setup", "staging", "weights"] + [f"F{l}:{p}" for l in range(3) for p in ("issued", "ready", "epilogue")]
          + ["F3:issued", "F3:ready", "F3:target", "F3:chunk0", "F3:chunk1", "F3:epilogue"]
          + [f"B{l}:{p}" for l in (3, 2, 1, 0) for p in ("issued", "ready", "epilogue")]
          + ["readout", "barrier", "gather"])
