@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
     load_x_row(xrow_of(gw, t));
   };
   // ---- part 1: nothing here reads or writes global memory, so under a programmatic dependent launch (launch_tc_tile)
-  // it runs while the previous kernel of the stream -- normally the previous train step -- is still in its tail ----
+  // it runs while the previous kernel of the stream is still in its tail ----
   griddep_launch_dependents();
   if (warp == 0) tmem_alloc(&tmem_slot, TRAIN ? 512 : 64 * NT);
   if (tid == 0) {
@@ -337,12 +337,15 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
     mbar_init(&tbar, 1);
     fence_barrier_init();
   }
-  {  // zero every activation / gradient buffer once: pad rows and pad channels stay zero
+  auto zero_buffers = [&]() {   // zero every activation / gradient buffer once: pad rows and pad channels stay zero
     const int act_bytes = L.ys;
     uint4* z = reinterpret_cast<uint4*>(smem);
     const uint4 zero = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < act_bytes / 16; i += kTileThreads) z[i] = zero;
-  }
+  };
+  // forward launches are programmatic by default: zero before the wait (under the predecessor); the train step is a
+  // normal launch unless B2H_PDL=2 (the wait is then a no-op) and zeroes under its own loads in flight instead
+  if (!TRAIN) zero_buffers();
   // ---- part 2: the previous kernel has completed and its writes (weights, Adam state, counters, inputs) are visible ----
   griddep_wait();
   B2H_STAMP();   // predecessor complete
@@ -383,6 +386,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
       if (p.epoch_dev) *p.epoch_dev += 1;
     }
   }
+  if (TRAIN) zero_buffers();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1085,13 +1089,16 @@ int launch_tc_tile(TcTileArgs& p, bool train, bool split, cudaStream_t stream) {
   // Grid barrier inside: a cooperative launch guarantees that all CTAs (<= 1 per SM) are co-resident.  B2H_NONCOOP=1
   // (measurement aid, read once) uses a plain launch of the same grid: identical residency on an otherwise idle GPU,
   // but nothing guarantees it when other kernels share the device.
-  // Programmatic dependent launch (B2H_PDL, default on): the kernel may start while its predecessor on the stream is
-  // still running; it allocates TMEM, initialises its barriers and zeroes its shared memory, then blocks in
-  // griddepcontrol.wait until the predecessor has completed (conv_tc_tile_kernel, part 1 / part 2).  Back-to-back steps
-  // (a captured graph of steps, the runner's loop) lose the launch gap and the set-up time between them.
+  // Programmatic dependent launch: the kernel may start while its predecessor on the stream is still running; it
+  // allocates TMEM, initialises its barriers and zeroes its shared memory, then blocks in griddepcontrol.wait until the
+  // predecessor has completed (conv_tc_tile_kernel, part 1 / part 2).  Measured on B200 (profiles/r2_pdl.txt): forward
+  // B=512x64 10.7 -> 9.2 us per batch, B=1 latency 8.7 -> 7.3 us; the train step gains 0.3 us of 27.4 (its 128 CTAs hold
+  // one SM each, so only 20 of the next step's CTAs find a free SM early, and the wait releases no sooner than a normal
+  // launch would start).  B2H_PDL (read once): unset / 1 = forward launches only, 2 = train steps too, 0 = none.
   static const bool noncoop = [] { const char* e = getenv("B2H_NONCOOP"); return e && e[0] == '1'; }();
-  static const bool pdl = [] { const char* e = getenv("B2H_PDL"); return !(e && e[0] == '0'); }();
+  static const int pdl_mode = [] { const char* e = getenv("B2H_PDL"); return e && e[0] >= '0' && e[0] <= '2' ? e[0] - '0' : 1; }();
   const bool coop = train && p.fuse.enabled && !noncoop;
+  const bool pdl = train ? pdl_mode == 2 : pdl_mode >= 1;
   if (pdl) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTileThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
