@@ -251,3 +251,19 @@ def test_pipelined_steps_slot_discipline(monkeypatch):
     FakeRunner.n_slots = 1
     with pytest.raises(RuntimeError):
         list(R.pipelined_steps(FakeRunner(), range(2)))
+
+
+def test_host_placement_helper_is_fail_soft():
+    """hostbind.bind_host_to_gpu: pure host plumbing for the N>1 launchers -- never raises, reports what it did."""
+    import os
+
+    from hand_pose_sl_b200 import hostbind
+
+    assert hostbind._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert hostbind._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    info = hostbind.bind_host_to_gpu(0)          # no GPU / one NUMA node here: says why and leaves the process alone
+    assert isinstance(info, dict) and "bound" in info
+    if not info["bound"]:
+        assert "why" in info
+        assert os.sched_getaffinity(0) == before

@@ -67,6 +67,41 @@ def test_no_normalize_no_left_hand_and_bf16_copy():
     assert torch.equal(o["input_kp_bf16"].float().cpu(), o["input_kp"].cpu().to(torch.bfloat16).float())
 
 
+def test_special_values_take_the_ieee_division_path():
+    """-0, denormals, tiny / huge magnitudes, inf and NaN inside a 4-frame group: the kernel's range test sends the whole
+    float4 through div.rn, everything else through the verified fast division -- both must equal the CPU's x / 1280."""
+    F = 256
+    pose, lh, rh = synthetic.synthetic_clip(F, seed=21)
+    specials = np.array([-0.0, 0.0, 1e-45, -1e-45, 1e-38, 3e-31, -9e-31, 1.1e-30, 9.9e29, -1.1e30, 3e38, -3.4e38,
+                         np.inf, -np.inf, np.nan, 1280.0, -1280.0, 1e-30, 1e30], dtype=np.float32)
+    rng = np.random.default_rng(5)
+    for arr in (pose, lh, rh):
+        flat = arr.reshape(F, -1)
+        for f in range(0, F, 3):                       # a few specials in most groups, on x / y / confidence alike
+            cols = rng.integers(0, flat.shape[1], size=4)
+            flat[f, cols] = rng.choice(specials, size=4)
+    starts = np.array([0, 3, 64, 129, 190], dtype=np.int64)
+    for dif in (True, False):
+        out = _run(pose, lh, rh, starts, 64, dif_encoding=dif)
+        want = oracle.preprocess_windows(pose, lh, rh, starts, 64, dif_encoding=dif)
+        for k in KEYS:
+            a, b = out[k], want[k]
+            same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b)) if a.dtype == np.float32 else (a == b)
+            assert same.all(), (k, dif, int((~same).sum()))
+
+
+@pytest.mark.parametrize("T", [1, 2, 3, 5, 7])
+def test_tiny_windows_cross_group_boundaries(T):
+    """Windows shorter than / not a multiple of the 4-frame group: every group mixes windows (per-slot walk)."""
+    pose, lh, rh = synthetic.synthetic_clip(97, seed=T)
+    starts = np.array([0, 4, 8, 93, 96, 40, 41, 42, 43], dtype=np.int64)
+    for pad in ("repeat_first", "zeros"):
+        out = _run(pose, lh, rh, starts, T, pad_mode=pad)
+        want = oracle.preprocess_windows(pose, lh, rh, starts, T, oracle.PAD_REPEAT_FIRST if pad == "repeat_first" else oracle.PAD_ZEROS)
+        for k in KEYS:
+            assert np.array_equal(out[k], want[k]), (k, T, pad)
+
+
 @pytest.mark.parametrize("tag", ["h5short", "h5long"])
 def test_h5_rows_golden(tag):
     g = load_golden("preprocess.npz")
