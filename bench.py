@@ -305,19 +305,29 @@ def main():
     # runner.pipelined_steps: batch i+1 travels on a copy stream while step i computes (what a prefetching DataLoader
     # gives the reference loop); the loss of every step is read on the host inside the loop (one step behind the launch).
     from hand_pose_sl_b200.runner import pipelined_steps
-    e2e_steps = 200
+    # Five back-to-back segments of 400 steps; the reported figure is the MEDIAN segment (a shared host's PCIe / memory
+    # traffic moves single short segments by tens of percent), all five are listed.
+    e2e_steps, e2e_segments = 400, 5
     h2d = int(staged[0].numel())
     for _ in pipelined_steps(runner, (staged[i % N_SLOTS] for i in range(10))):
         pass
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
+    seg_dt = []
     n_p, loss_val = 0, float("nan")
-    for loss_val in pipelined_steps(runner, (staged[i % N_SLOTS] for i in range(e2e_steps))):
-        n_p += 1
-    torch.cuda.synchronize()
-    e2e_dt = time.perf_counter() - t0
+    for _seg in range(e2e_segments):
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        n_p = 0
+        for loss_val in pipelined_steps(runner, (staged[i % N_SLOTS] for i in range(e2e_steps))):
+            n_p += 1
+        torch.cuda.synchronize()
+        seg_dt.append(time.perf_counter() - t0)
+    if world > 1:                                             # a segment takes as long as its slowest rank
+        t = torch.tensor(seg_dt, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        seg_dt = [float(v) for v in t.tolist()]
+    e2e_dt = sorted(seg_dt)[len(seg_dt) // 2]
     # sequential variant (copy, then step, then read) for reference
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -327,11 +337,12 @@ def main():
     torch.cuda.synchronize()
     seq_dt = (time.perf_counter() - t0) / 50
     if world > 1:
-        t = torch.tensor([e2e_dt, seq_dt], device=dev, dtype=torch.float64)
+        t = torch.tensor([seq_dt], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt, seq_dt = float(t[0].item()), float(t[1].item())
+        seq_dt = float(t[0].item())
     e2e = {"value": n_p * B_TRAIN * T * world / e2e_dt, "unit": "frames/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": 4, "steps": n_p,
+           "d2h_bytes_per_step": 4, "steps": n_p, "segments": e2e_segments,
+           "segment_us_per_step": [round(v / max(n_p, 1) * 1e6, 2) for v in seg_dt], "statistic": "median segment",
            "api": "runner.pipelined_steps(runner, runner.host_stage(batch) buffers): per step ONE cudaMemcpyAsync of the pinned batch, "
                   "the step, and the loss read on the host (the kernel stores it into pinned host memory; read one step behind the launch)",
            "mode": "pipelined (double-buffered H2D on a copy stream)", "input_dtype": str(x_dt).replace("torch.", ""),
