@@ -946,7 +946,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) conv_tc_tile_kernel(TcTileArg
             // push my slot to every rank, then collect the world's slots for the same j from my own buffer and sum them
             // in rank order (identical arithmetic on every rank).  With a multicast (NVLS) mapping of the exchange
             // buffers ONE multimem.st is replicated by the NVSwitch into every rank's buffer; otherwise W unicast
-            // 8-byte stores (coalesced per warp, fire-and-forget over NVLink).
+            // 4-byte stores (coalesced per warp, fire-and-forget over NVLink).  The word is its own arrival flag: the
+            // reader's buffer holds the sentinel until the value lands, and the reader re-arms it after use.
             uint32_t word = __float_as_uint(gr);
             if (word == kDpSentinel) word = 0x7FC00000u;               // (a NaN gradient stays a NaN, never the sentinel)
             if (f.mc_buf) {
