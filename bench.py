@@ -588,6 +588,32 @@ def main():
                                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                                "frac": gbs / pk["hbm_gbs"], "traffic": ptraffic,
                                                "note": "CUDA-graph replay, outputs reused; 314 MB moved per launch > 126 MB L2"}}
+            # ---------------- K0, packed H5 rows (TextPoseH5Dataset.array2item): same kernel, 150-float rows ----------------
+            try:
+                rows = torch.randn(F, 150, device=dev) * 300 + 600
+                rows[:, 100:] = torch.rand(F, 50, device=dev)
+                h5o = pre.from_h5_rows(rows, starts, F)
+                torch.cuda.synchronize()
+                hgraph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(hgraph):
+                    for _ in range(4):
+                        h5o = pre.from_h5_rows(rows, starts, F)
+                hgraph.replay()
+                torch.cuda.synchronize()
+                ev0.record()
+                for _ in range(preps // 4):
+                    hgraph.replay()
+                ev1.record()
+                torch.cuda.synchronize()
+                h_ms = ev0.elapsed_time(ev1) / preps
+                h_gbs = F * 1200 / (h_ms * 1e-3) / 1e9
+                line["preprocess_h5"] = {"metric": "body2hand_preprocess_frames_per_sec", "value": F / (h_ms * 1e-3), "unit": "frames/s",
+                                         "ms_per_launch": h_ms, "workload": f"{F} packed H5 rows (600 B read + 600 B written per frame)",
+                                         "roofline": {"bound": "hbm", "achieved": h_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                                      "frac": h_gbs / pk["hbm_gbs"], "traffic": None}}
+                del rows, h5o, hgraph
+            except Exception as ex:   # noqa: BLE001
+                line["preprocess_h5"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
         if not args.skip_extras:
             # ---------------- config 5: streaming K0 -> K1 over 1 h of frames (stride 64 and 16) ----------------
             # K0 runs ONCE per unique frame and writes only what the net reads (a (F,12,2) bf16 stream); the forward reads
