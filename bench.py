@@ -385,6 +385,15 @@ def main():
         line["dp_parity"] = dp_parity
         line["comm_nranks"] = int(runner.peers_seen)
 
+    if world > 1 and launches_per_step == 1:
+        # per-GPU roofline of the one fused kernel (its in-kernel gradient exchange included); cpu_baseline is N=1 only
+        k_ms = ms / timed_steps
+        tfl = TRAIN_FLOP_PER_WINDOW * B_TRAIN / (k_ms * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "achieved": tfl, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": tfl / pk["tflops"],
+                            "traffic": None, "kernel": "conv_tc_tile_kernel<train> (data-parallel tail)", "kernel_ms": k_ms,
+                            "algorithmic_flop_per_launch": TRAIN_FLOP_PER_WINDOW * B_TRAIN,
+                            "peak_source": pk["source"] + ", bf16 dense sustained",
+                            "note": "per GPU: one cooperative launch per step per rank, peer-memory gradient exchange inside it"}
     if rank == 0 and world == 1:
         # ---------------- roofline of the dominant kernel (fused fwd+loss+bwd), timed alone ----------------
         lib = _lib.load()
