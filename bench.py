@@ -181,6 +181,7 @@ def run_reference(args, rank):
 
 
 def main():
+    global B_TRAIN
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=400)
@@ -190,6 +191,8 @@ def main():
     ap.add_argument("--skip-extras", action="store_true", help="only the headline train-step number")
     ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "nccl"], help="multi-GPU gradient exchange")
     ap.add_argument("--no-multicast", action="store_true", help="p2p exchange: unicast stores even when an NVLS mapping exists")
+    ap.add_argument("--strong", action="store_true", help="strong scaling (SURVEY 8d config 4): the GLOBAL batch stays 256 windows, "
+                                                         "each of the N ranks trains 256/N; the default (and the driver's contract) is weak")
     ap.add_argument("--no-numa-bind", action="store_true", help="leave the rank's threads / pinned buffers where the OS puts them")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -199,6 +202,10 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    if args.strong:
+        if 256 % world:
+            raise SystemExit("--strong needs a rank count that divides 256")
+        B_TRAIN = 256 // world
 
     import torch
     import torch.distributed as dist
@@ -369,7 +376,8 @@ def main():
 
     line = {"metric": "body2hand_train_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / timed_steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if train_prec.startswith("fp32") else "bf16", "data": "synthetic",
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+            "dtype": "f32" if train_prec.startswith("fp32") else "bf16", "data": "synthetic",
             "repeats": repeats, "timed_steps": timed_steps, "timed_region_ms": ms,
             "config": {"workload": f"train step (fwd+mask+L1+bwd+Adam), batch {B_TRAIN}x{T} frames per GPU, C={C} (BASELINE config 3/4)",
                        "global_batch": B_TRAIN * world, "frames_per_window": T, "conv_channels": C,
@@ -682,6 +690,38 @@ def main():
                                   "path": "materialised windows"})
                 line["stream"][f"stride{stride}"] = entry
                 del sg, frs, so
+            # ---- the same pipeline over 8 h of frames: window views only; the clip is the 2 h clip x 4 ----
+            if fwd_prec == "bf16":
+                try:
+                    F8 = 4 * F
+                    lp_, ll_, lr_ = (t_.repeat(4, 1, 1) for t_ in (tp, tl, tr))
+                    pre_v = b2h.PreprocessRightHand()
+                    stream8 = pre_v.frame_stream(lp_, ll_, lr_)
+                    long_run = {"frames": F8}
+                    for stride in (64, 16):
+                        st_ = torch.from_numpy(b2h.sliding_window_starts(F8 - T + 1, T, stride)).to(dev)
+                        Wn = st_.numel()
+                        yv = fmodel.predict_windows(stream8, st_, T, denormalize=1280.0)
+                        torch.cuda.synchronize()
+                        sg = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(sg):
+                            for _ in range(2):
+                                pre_v.frame_stream(lp_, ll_, lr_, out=stream8)
+                                fmodel.predict_windows(stream8, st_, T, denormalize=1280.0, out=yv)
+                        sg.replay(); torch.cuda.synchronize()
+                        ev0.record()
+                        for _ in range(3):
+                            sg.replay()
+                        ev1.record()
+                        torch.cuda.synchronize()
+                        l_ms = ev0.elapsed_time(ev1) / 6
+                        long_run[f"stride{stride}"] = {"windows": Wn, "ms": l_ms, "unique_frames_per_sec": F8 / (l_ms * 1e-3),
+                                                       "window_frames_per_sec": Wn * T / (l_ms * 1e-3)}
+                        del sg, yv, st_
+                    line["stream"]["clip_8h"] = long_run
+                    del lp_, ll_, lr_, stream8
+                except Exception as ex:   # noqa: BLE001
+                    line["stream"]["clip_8h"] = {"error": f"{type(ex).__name__}: {ex}"[:200]}
         # ---------------- CPU baseline (reference path on this box's host cores) ----------------
         line["cpu_baseline"], _, _ = cpu_reference_arm(200, 2, budget_s=15.0)
         if not args.skip_extras:
