@@ -9,12 +9,13 @@
 //   BuildRightHandItem                       body2hand/src/steps/utils.py:261-277
 //   TextPoseH5Dataset.array2item             ...text_pose_dataset.py:587-612
 //
-// Design: one warp owns 4 consecutive window slots.  4 OpenPose frames are 1200 B (pose) +
-// 2 x 1008 B (hands): all three are 16-B multiples, so an aligned 4-frame group is moved
-// HBM -> shared memory with coalesced 128-bit loads (201 float4 per warp, all issued before the first
-// use), the wrist / neck references are shared through the staged tile, and the six output rows of the
-// 4 slots (162 float4) go back with coalesced 128-bit stores.  Padded / unaligned groups take a scalar
-// path inside the same kernel (warp-uniform branch).  IEEE sub.rn then div.rn: no reciprocal, no FMA.
+// Design: one warp owns 4 consecutive window slots.  4 OpenPose frames are 1200 B (pose) + 2 x 1008 B (hands): all three
+// are 16-B multiples, so an aligned 4-frame group travels HBM -> shared memory as three TMA bulk copies into the warp's
+// double buffer, one group ahead of the compute (mbarrier completion).  The wrist / neck references are shared through
+// the staged tile; a per-CTA gather table says where every output element's source and reference sit, and the six output
+// rows of the 4 slots (162 float4) go back with coalesced 128-bit streaming stores.  Padded / unaligned groups are filled
+// by the lanes inside the same kernel (warp-uniform branch).  IEEE sub.rn then div.rn: no reciprocal shortcut that is not
+// verified bit-exact, no FMA contraction across the two.
 #include "b2h_common.cuh"
 #define B2H_TC_NO_STATUS
 #include "b2h_tc.cuh"   // mbarrier + 1-D TMA bulk copy helpers
