@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, prec, kind, exchange, ret):
+def _worker(rank, world, port, prec, kind, exchange, C, ret):
     sys.path.insert(0, ROOT)
     import hand_pose_sl_b200 as b2h
     from hand_pose_sl_b200 import parallel, synthetic
@@ -27,7 +27,7 @@ def _worker(rank, world, port, prec, kind, exchange, ret):
         B, T, steps = 16 * world, 64, 4
         batch = synthetic.model_batch(B, T, seed=77, ragged=True)
         torch.manual_seed(0)
-        model = b2h.ConvModel(30, "ReLU", False, precision=prec).to(dev)
+        model = b2h.ConvModel(C, "ReLU", False, precision=prec).to(dev)
         opt = b2h.FusedAdam(model.parameters(), lr=2e-4)
         tr = parallel.DataParallelTrainer(model, opt, B // world, T, kind, exchange=exchange)
         assert tr.exchange == exchange
@@ -52,7 +52,7 @@ def _worker(rank, world, port, prec, kind, exchange, ret):
         tr.check_status()
         if rank == 0:
             torch.manual_seed(0)
-            ref = b2h.ConvModel(30, "ReLU", False, precision=prec).to(dev)
+            ref = b2h.ConvModel(C, "ReLU", False, precision=prec).to(dev)
             ropt = b2h.FusedAdam(ref.parameters(), lr=2e-4)
             rr = TrainStepRunner(ref, ropt, B, T, kind)
             rr.load(batch, non_blocking=False)
@@ -77,16 +77,27 @@ def _worker(rank, world, port, prec, kind, exchange, ret):
         os._exit(0 if ret.get(rank) == "ok" else 1)
 
 
-@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
-@pytest.mark.parametrize("prec,kind", [("fp32", "L1"), ("bf16", "L1"), ("bf16", "confL1")])
-def test_data_parallel_matches_single_gpu(prec, kind, exchange):
+def _spawn(prec, kind, exchange, C):
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
-    port = 29600 + (os.getpid() % 1000) + (7 if exchange == "p2p" else 0) + (len(prec) + len(kind)) * 11
+    port = 29600 + (os.getpid() % 1000) + (7 if exchange == "p2p" else 0) + (len(prec) + len(kind)) * 11 + C
     ret = mp.Manager().dict()
     try:
-        mp.spawn(_worker, args=(world, port, prec, kind, exchange, ret), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, prec, kind, exchange, C, ret), nprocs=world, join=True)
     except Exception as e:  # noqa: BLE001  (a worker exited non-zero: its message is in `ret`)
         assert False, (str(e)[:300], dict(ret))
     assert len(ret) == world and all(v == "ok" for v in ret.values()), dict(ret)
+
+
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+@pytest.mark.parametrize("prec,kind", [("fp32", "L1"), ("bf16", "L1"), ("bf16", "confL1")])
+def test_data_parallel_matches_single_gpu(prec, kind, exchange):
+    _spawn(prec, kind, exchange, 30)
+
+
+@pytest.mark.parametrize("prec,C", [("fp32-ffma", 30), ("bf16", 64)])
+def test_data_parallel_three_launch_path(prec, C):
+    """Shapes without the one-launch step (CUDA-core fp32 mode, wide models): forward/backward -> slice reduction into
+    the symmetric buffer -> `adam_dp_kernel` reading every peer's gradients over NVLink (b2h_train_step_dp's other branch)."""
+    _spawn(prec, "L1", "p2p", C)
