@@ -222,7 +222,11 @@ def main():
     os.dup2(2, 1)
     # before the first pinned allocation: the rank's threads and staging buffers go to its GPU's NUMA node
     from hand_pose_sl_b200.hostbind import bind_host_to_gpu
-    host_numa = {"bound": False, "why": "--no-numa-bind"} if args.no_numa_bind else bind_host_to_gpu(local_rank)
+    # (N = 1 is left alone: the same process times the CPU baseline afterwards on ALL host cores)
+    if args.no_numa_bind or world == 1:
+        host_numa = {"bound": False, "why": "--no-numa-bind" if args.no_numa_bind else "single process"}
+    else:
+        host_numa = bind_host_to_gpu(local_rank)
     if world > 1:
         sys.stderr.write(f"[bench] rank {rank}: host placement {host_numa}\n")
     torch.cuda.set_device(local_rank)
