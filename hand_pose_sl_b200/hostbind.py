@@ -11,8 +11,9 @@ the `numactl --cpunodebind=N --preferred=N` a launcher script would apply, taken
     (`cudaHostAlloc` takes its pages under the caller's policy) are node-local even when the threads could not move.
 
 Call it before the first pinned allocation, from the thread that will create the process's other threads (the affinity
-is per thread and inherited at thread creation: pools that already exist keep theirs).  Pure host plumbing: nothing here touches the data path, and every failure
-(no NVML, no sysfs entry, single-node box) returns a dict saying why instead of raising.
+is per thread and inherited at thread creation: pools that already exist keep theirs).  Pure host plumbing: nothing here
+touches the data path, and every failure (no NVML, no sysfs entry, single-node box) returns a dict saying why instead of
+raising.
 The reference has no counterpart: it is a single process (`body2hand/src/run.py`) with a torch `DataLoader`.
 """
 from __future__ import annotations
